@@ -1,0 +1,90 @@
+"""Host caller of the backward kernels - the restatement of ``_flash_attn_backward``
+(reference src/backward/caller.py:14-178): delta preprocess, fused dK/dV/dQ kernel, dQ conversion."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .forward import _reject_out_of_scope, _stream_ptr, encode_dtype
+
+# Process-wide default for how dQ contributions are summed. True: fixed key-block order, bit-identical
+# run to run (what the reference's atomics-free kernel guarantees, src/backward/kernel.py:154-182).
+# False: arrival order ("atomic fast mode").
+_DETERMINISTIC = True
+
+
+def set_deterministic(flag: bool) -> None:
+    global _DETERMINISTIC
+    _DETERMINISTIC = bool(flag)
+
+
+def is_deterministic() -> bool:
+    return _DETERMINISTIC
+
+
+def _flash_attn_backward(
+    dO: Tensor,  # [batch_size, seqlen_q, nheads_q, head_dim]
+    q: Tensor,  # [batch_size, seqlen_q, nheads_q, head_dim]
+    k: Tensor,  # [batch_size, seqlen_k, nheads_kv, head_dim]
+    v: Tensor,  # [batch_size, seqlen_k, nheads_kv, head_dim]
+    bias: Optional[Tensor],
+    attention_mask: Optional[Tensor],
+    o: Tensor,  # [batch_size, seqlen_q, nheads_q, head_dim]
+    lse: Tensor,  # [batch_size, nheads_q, max_seqlen_q_rounded]
+    dropout_p: float,
+    causal: bool,
+    softmax_scale: Optional[float],
+    dropout_seed: Optional[int],
+    deterministic: Optional[bool] = None,
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Returns ``(dq, dk, dv)`` like src/backward/caller.py:178: ``dq`` is fp32 ``[B, Sq, Hq, D]``
+    (src/backward/caller.py:86), ``dk``/``dv`` are ``[B, Sk, Hkv, D]`` in the input dtype with the GQA
+    head-group sum (src/backward/caller.py:163-165) already applied inside the kernel."""
+    _reject_out_of_scope(attention_mask, bias, dropout_p)
+    dO = dO.contiguous() if dO.stride(-1) != 1 else dO
+    batch_size, seqlen_q, nheads_q, head_dim = q.shape
+    _, seqlen_k, nheads_kv, _ = k.shape
+    max_seqlen_q_rounded = math.ceil(seqlen_q / 128) * 128
+    softmax_scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
+    # same checks as src/backward/caller.py:51-53
+    assert nheads_q % nheads_kv == 0, f"{nheads_q = } is not divisible by {nheads_kv =}"
+    assert lse.shape == (batch_size, nheads_q, max_seqlen_q_rounded)
+    assert q.stride(-1) == k.stride(-1) == v.stride(-1) == o.stride(-1) == 1
+    assert dO.shape == q.shape and o.shape == q.shape
+    assert q.is_cuda and k.is_cuda and v.is_cuda and o.is_cuda and dO.is_cuda and lse.is_cuda
+    assert q.dtype == k.dtype == v.dtype == o.dtype == dO.dtype, "All tensors must have the same type"
+    assert lse.dtype == torch.float32 and lse.is_contiguous()
+    det = _DETERMINISTIC if deterministic is None else bool(deterministic)
+
+    lib = _lib.load()
+    dt = encode_dtype(q)
+    with torch.cuda.device(q.device):
+        stream = _stream_ptr(q.device)
+        delta = torch.empty_like(lse)
+        dq = torch.empty_like(q, dtype=torch.float32)
+        dk = torch.empty_like(k)
+        dv = torch.empty_like(v)
+        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, int(det))
+        workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+
+        code = lib.fa2_sm100_bwd_delta(
+            o.data_ptr(), dO.data_ptr(), delta.data_ptr(), batch_size, nheads_q, seqlen_q, head_dim,
+            _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt, stream)
+        _lib.check(code, "fa2_sm100_bwd_delta")
+        code = lib.fa2_sm100_bwd(
+            dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+            dk.data_ptr(), dv.data_ptr(), workspace.data_ptr(), ws_bytes,
+            batch_size, nheads_q, nheads_kv, seqlen_q, seqlen_k, head_dim,
+            _lib.strides3(dO), _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
+            _lib.strides3(dk), _lib.strides3(dv),
+            max_seqlen_q_rounded, softmax_scale, int(bool(causal)), int(det), dt, stream)
+        _lib.check(code, "fa2_sm100_bwd")
+        code = lib.fa2_sm100_dq_convert(
+            workspace.data_ptr(), dq.data_ptr(), batch_size, nheads_q, seqlen_q, head_dim,
+            _lib.strides3(dq), softmax_scale, _lib.DTYPE_FP32, stream)
+        _lib.check(code, "fa2_sm100_dq_convert")
+    return dq, dk, dv

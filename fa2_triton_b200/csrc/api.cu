@@ -1,0 +1,242 @@
+// C ABI of libfa2_sm100.so (see include/fa2_sm100.h): argument validation, TMA tensor-map encoding and
+// kernel launches. Host-side restatement of what the reference's callers do around their Triton launches
+// (src/forward/caller.py:33-116, src/backward/caller.py:46-160), minus allocation - the caller owns memory.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/fa2_sm100.h"
+#include "fa2_kernels.cuh"
+
+namespace {
+
+thread_local char g_last_error[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(static_cast<int>(e), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+bool is_16bit(int dtype) { return dtype == FA2_DTYPE_FP16 || dtype == FA2_DTYPE_BF16; }
+
+// [B, S, H, D] tensor with (batch, head, seq) element strides -> 4-D map (D, S, H, B), box (64, box_rows, 1, 1),
+// 128-byte swizzle, zero fill for out-of-bounds rows.
+int make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype, int B, int S, int H, int D, const int64_t strides[3],
+                   int box_rows, const char* name) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(FA2_E_NO_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  if (!ptr) return fail(FA2_E_NULL_POINTER, "%s: null pointer", name);
+  if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0) return fail(FA2_E_BAD_ALIGNMENT, "%s: base not 16-byte aligned", name);
+  for (int i = 0; i < 3; ++i) {
+    if (strides[i] < 0 || (strides[i] * 2) % 16 != 0)
+      return fail(FA2_E_BAD_ALIGNMENT, "%s: stride[%d]=%lld elements is not a non-negative multiple of 8", name, i,
+                  static_cast<long long>(strides[i]));
+  }
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(B)};
+  // a size-1 dimension may carry a zero stride in torch; TMA wants something positive and 16-byte granular
+  auto fix = [&](int64_t s) { return static_cast<cuuint64_t>((s > 0 ? s : static_cast<int64_t>(D)) * 2); };
+  const cuuint64_t gstride[3] = {fix(strides[2]), fix(strides[1]), fix(strides[0])};
+  const cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(box_rows), 1u, 1u};
+  const cuuint32_t estride[4] = {1u, 1u, 1u, 1u};
+  const CUtensorMapDataType dt = dtype == FA2_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, 4, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(static_cast<int>(r), "%s: cuTensorMapEncodeTiled failed with CUresult %d", name, static_cast<int>(r));
+  return 0;
+}
+
+int check_common(int B, int Hq, int Hkv, int Sq, int Sk, int D, int dtype) {
+  if (!is_16bit(dtype)) return fail(FA2_E_UNSUPPORTED_DTYPE, "dtype code %d: only 16 (fp16) and 17 (bf16) are supported", dtype);
+  if (D != 64 && D != 128) return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: this build supports 64 and 128", D);
+  if (B < 1 || Hq < 1 || Hkv < 1 || Sq < 1 || Sk < 1) return fail(FA2_E_BAD_SHAPE, "non-positive dimension");
+  if (Hq % Hkv != 0) return fail(FA2_E_BAD_SHAPE, "nheads_q = %d is not divisible by nheads_kv = %d", Hq, Hkv);
+  if (Hq > 65535 || B > 65535) return fail(FA2_E_BAD_SHAPE, "batch and head counts must fit a grid dimension");
+  return 0;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" {
+
+int fa2_sm100_version(void) { return FA2_SM100_ABI_VERSION; }
+
+const char* fa2_sm100_last_error(void) { return g_last_error; }
+
+int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int Sq,
+                  int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                  const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
+                  void* stream) {
+  if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
+  if (!lse) return fail(FA2_E_NULL_POINTER, "lse: null pointer");
+  if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
+  if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
+  CUtensorMap tq, tk, tv, to;
+  if (int e = make_tmap_bshd(&tq, q, dtype, B, Sq, Hq, D, q_strides, 128, "q")) return e;
+  if (int e = make_tmap_bshd(&tk, k, dtype, B, Sk, Hkv, D, k_strides, 128, "k")) return e;
+  if (int e = make_tmap_bshd(&tv, v, dtype, B, Sk, Hkv, D, v_strides, 128, "v")) return e;
+  if (int e = make_tmap_bshd(&to, o, dtype, B, Sq, Hq, D, o_strides, 128, "o")) return e;
+  fa2::FwdParams p{};
+  p.lse = lse;
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk;
+  p.lse_stride = static_cast<int>(lse_row_stride);
+  p.scale_log2 = softmax_scale * kLog2e;
+  p.causal = causal ? 1 : 0;
+  p.n_pairs = (Sq + 255) / 256;
+  cudaError_t ce = fa2::launch_fwd(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, to, p, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_fwd launch");
+  return 0;
+}
+
+int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, int Hq, int Sq, int D,
+                        const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride, int dtype,
+                        void* stream) {
+  if (int e = check_common(B, Hq, Hq, Sq, 1, D, dtype)) return e;
+  if (!o || !dout || !delta) return fail(FA2_E_NULL_POINTER, "o / dout / delta: null pointer");
+  if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
+  if (reinterpret_cast<uintptr_t>(o) % 16 || reinterpret_cast<uintptr_t>(dout) % 16)
+    return fail(FA2_E_BAD_ALIGNMENT, "o / dout: base not 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    if (o_strides[i] % 8 || do_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "o / dout: strides must be multiples of 8 elements");
+  fa2::DeltaParams p{};
+  p.o = o; p.dout = dout; p.delta = delta;
+  p.B = B; p.Hq = Hq; p.Sq = Sq; p.D = D;
+  p.lse_stride = static_cast<int>(lse_row_stride);
+  for (int i = 0; i < 3; ++i) { p.o_strides[i] = o_strides[i]; p.do_strides[i] = do_strides[i]; }
+  cudaError_t ce = fa2::launch_delta(dtype == FA2_DTYPE_BF16, p, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd_delta launch");
+  return 0;
+}
+
+size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic) {
+  (void)Sk;
+  (void)deterministic;
+  if (B < 1 || Hq < 1 || Sq < 1 || D < 1) return 0;
+  const size_t sq_pad = static_cast<size_t>(round_up(Sq, 128));
+  const size_t accum = static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float);
+  const size_t sem = static_cast<size_t>(B) * Hq * (sq_pad / 128) * sizeof(int);
+  return accum + ((sem + 15) / 16) * 16;
+}
+
+int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v, const float* lse, const float* delta,
+                  void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int Hq, int Hkv, int Sq, int Sk,
+                  int D, const int64_t do_strides[3], const int64_t q_strides[3], const int64_t k_strides[3],
+                  const int64_t v_strides[3], const int64_t dk_strides[3], const int64_t dv_strides[3],
+                  int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype, void* stream) {
+  if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
+  if (!lse || !delta || !workspace) return fail(FA2_E_NULL_POINTER, "lse / delta / workspace: null pointer");
+  if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
+  if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
+  const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, Sk, D, deterministic);
+  if (workspace_bytes < need)
+    return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FA2_E_BAD_ALIGNMENT, "workspace not 16-byte aligned");
+  CUtensorMap tq, tk, tv, tdo, tdk, tdv;
+  if (int e = make_tmap_bshd(&tq, q, dtype, B, Sq, Hq, D, q_strides, 128, "q")) return e;
+  if (int e = make_tmap_bshd(&tk, k, dtype, B, Sk, Hkv, D, k_strides, 128, "k")) return e;
+  if (int e = make_tmap_bshd(&tv, v, dtype, B, Sk, Hkv, D, v_strides, 128, "v")) return e;
+  if (int e = make_tmap_bshd(&tdo, dout, dtype, B, Sq, Hq, D, do_strides, 128, "dout")) return e;
+  if (int e = make_tmap_bshd(&tdk, dk, dtype, B, Sk, Hkv, D, dk_strides, 128, "dk")) return e;
+  if (int e = make_tmap_bshd(&tdv, dv, dtype, B, Sk, Hkv, D, dv_strides, 128, "dv")) return e;
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t ce = cudaMemsetAsync(workspace, 0, need, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd workspace memset");
+
+  const int sq_pad = round_up(Sq, 128);
+  fa2::BwdParams p{};
+  p.lse = lse; p.delta = delta;
+  p.dq_accum = static_cast<float*>(workspace);
+  p.dq_sem = reinterpret_cast<int*>(static_cast<char*>(workspace) + static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float));
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk;
+  p.lse_stride = static_cast<int>(lse_row_stride);
+  p.sq_pad = sq_pad;
+  p.softmax_scale = softmax_scale;
+  p.scale_log2 = softmax_scale * kLog2e;
+  p.causal = causal ? 1 : 0;
+  p.deterministic = deterministic ? 1 : 0;
+  ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, tdk, tdv, p, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
+  return 0;
+}
+
+int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq, int D, const int64_t dq_strides[3],
+                         float softmax_scale, int out_dtype, void* stream) {
+  if (!workspace || !dq) return fail(FA2_E_NULL_POINTER, "workspace / dq: null pointer");
+  if (D != 64 && D != 128) return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: this build supports 64 and 128", D);
+  if (B < 1 || Hq < 1 || Sq < 1) return fail(FA2_E_BAD_SHAPE, "non-positive dimension");
+  if (out_dtype != FA2_DTYPE_FP16 && out_dtype != FA2_DTYPE_BF16 && out_dtype != FA2_DTYPE_FP32)
+    return fail(FA2_E_UNSUPPORTED_DTYPE, "out_dtype code %d: expected 16, 17 or 32", out_dtype);
+  if (reinterpret_cast<uintptr_t>(dq) % 16) return fail(FA2_E_BAD_ALIGNMENT, "dq: base not 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    if (dq_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "dq: strides must be multiples of 8 elements");
+  fa2::DqConvertParams p{};
+  p.dq_accum = static_cast<const float*>(workspace);
+  p.dq = dq;
+  p.B = B; p.Hq = Hq; p.Sq = Sq; p.D = D;
+  p.sq_pad = round_up(Sq, 128);
+  for (int i = 0; i < 3; ++i) p.dq_strides[i] = dq_strides[i];
+  p.scale = softmax_scale;
+  p.out_dtype = out_dtype;
+  cudaError_t ce = fa2::launch_dq_convert(p, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_dq_convert launch");
+  return 0;
+}
+
+int fa2_sm100_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_mode, int b_mode, int dtype,
+                               void* stream) {
+  if (!is_16bit(dtype)) return fail(FA2_E_UNSUPPORTED_DTYPE, "dtype code %d", dtype);
+  if ((N != 64 && N != 128) || (K != 64 && K != 128)) return fail(FA2_E_BAD_SHAPE, "N and K must be 64 or 128");
+  if (a_mode < 0 || a_mode > 2 || b_mode < 0 || b_mode > 1) return fail(FA2_E_BAD_SHAPE, "bad operand mode");
+  if (!a || !b || !d) return fail(FA2_E_NULL_POINTER, "null pointer");
+  CUtensorMap ta, tb;
+  // A as [1, 128, 1, K]: strides (batch, head, seq) = (128*K, K, K)
+  const int64_t sa[3] = {128LL * K, K, K};
+  if (int e = make_tmap_bshd(&ta, a, dtype, 1, 128, 1, K, sa, 128, "probe a")) return e;
+  if (b_mode == 0) {
+    const int64_t sb[3] = {static_cast<int64_t>(N) * K, K, K};
+    if (int e = make_tmap_bshd(&tb, b, dtype, 1, N, 1, K, sb, N, "probe b")) return e;
+  } else {
+    const int64_t sb[3] = {static_cast<int64_t>(N) * K, N, N};
+    if (int e = make_tmap_bshd(&tb, b, dtype, 1, K, 1, N, sb, K, "probe b")) return e;
+  }
+  fa2::ProbeParams p{};
+  p.a = a; p.b = b; p.d = d; p.N = N; p.K = K; p.a_mode = a_mode; p.b_mode = b_mode;
+  cudaError_t ce = fa2::launch_probe(dtype == FA2_DTYPE_BF16, ta, tb, p, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_debug_umma_probe launch");
+  return 0;
+}
+
+}  // extern "C"

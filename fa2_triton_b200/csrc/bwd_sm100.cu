@@ -1,0 +1,667 @@
+// FlashAttention-2 backward for sm_100a (B200).
+//
+//   fa2_delta_kernel      delta = rowsum(O * dO)                 <- `_compute_delta`  src/backward/compute_delta.py:18-73
+//   fa2_bwd_kernel        dK, dV and the dQ partial sums         <- `_bwd_kernel`     src/backward/kernel.py:65-182
+//                                                                   (compute_dkdv.py:8-112, compute_dq.py:8-78)
+//   fa2_dq_convert_kernel fp32 dQ accumulator -> caller's dQ     <- the fp32 `dq` of  src/backward/caller.py:86
+//
+// Arithmetic contract: P = exp2(S*c - LSE2) recomputed from the saved log2-domain LSE,
+// dV = P^T dO with P rounded to the input dtype, dP = dO V^T, dS = P o (dP - delta) rounded to the input dtype,
+// dK = dS^T Q * scale, dQ = dS K * scale. (The reference folds `scale` into dS before rounding; we round dS and
+// apply `scale` to the fp32 sums - the same value up to one rounding of a 16-bit number.)
+//
+// Unlike the reference (one program per K/V block for dK/dV plus one program per Q block that recomputes
+// everything for dQ, 7 matmuls) this kernel does the minimal 5 matmuls: one CTA owns a 128-row K/V block, walks
+// the query blocks that see it and adds its dQ contribution into an fp32 accumulator with TMA bulk reductions.
+// Deterministic mode serialises those additions per query tile in a fixed key-block order with a ticket.
+//
+// CTA = 16 warps:
+//   warps 0-3 / 4-7 : compute warpgroups; thread = key row (TMEM lane), warpgroup w owns query columns [64w, 64w+64)
+//   warps 8-11      : dQ drain: TMEM -> registers -> smem staging -> cp.reduce.async.bulk (fp32 add) into global
+//   warp 12         : MMA issuer          warp 13 : TMA producer          warps 14-15 : idle
+// TMEM (512 columns): S^T / P^T [0,128) | dV [128,128+D) | dK [256,256+D) | dP^T, then dQ [384,512)
+// MMA issue order per query block i:  dV(i) | dP(i) | S(i+1) | dK(i) | dQ(i)
+#include "fa2_kernels.cuh"
+#include "ptx.cuh"
+
+namespace fa2 {
+
+namespace {
+
+constexpr int kBlk = 128;  // rows per Q block and per K/V block
+constexpr int kBwdThreads = 512;
+// register re-partition (setmaxnreg): 3 math warpgroups x 128 x 152 + 1 issue warpgroup x 128 x 56 = 65536
+constexpr int kRegsMath = 152;
+constexpr int kRegsIssue = 56;
+
+template <int D>
+struct BwdSmem {
+  static constexpr int kTileBytes = kBlk * D * 2;     // K, V, Q, dO tiles
+  static constexpr int kDsBytes = kBlk * kBlk * 2;    // dS^T tile: 2 sub-tiles [128 kv x 64 q]
+  static constexpr int kPanelBytes = kBlk * 64 * 4;   // one dQ panel: [128 q x 64 d] fp32
+  static constexpr bool kStagingAliasesDO = (D == 128);
+  static constexpr int kKOff = 0;
+  static constexpr int kVOff = kKOff + kTileBytes;
+  static constexpr int kQOff = kVOff + kTileBytes;          // 2 stages
+  static constexpr int kDOOff = kQOff + 2 * kTileBytes;     // 2 stages
+  static constexpr int kDsOff = kDOOff + 2 * kTileBytes;
+  static constexpr int kStageOff = kDsOff + kDsBytes;       // dQ staging (only when not aliased)
+  static constexpr int kLseOff = kStageOff + (kStagingAliasesDO ? 0 : kPanelBytes);  // 2 x 512 B
+  static constexpr int kDeltaOff = kLseOff + 2 * kBlk * 4;                            // 2 x 512 B
+  static constexpr int kBarOff = kDeltaOff + 2 * kBlk * 4;
+  static constexpr int kNumBars = 16;
+  static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
+  static constexpr int kBytes = kTmemSlotOff + 16;
+  static_assert(kBytes <= 232448, "backward smem budget exceeded");
+};
+
+enum BwdBar {
+  kKvFull = 0,
+  kQFull = 1,    // [2]
+  kQEmpty = 3,   // [2]
+  kDoFull = 5,   // [2]
+  kDoEmpty = 7,  // [2]
+  kSFull = 9,
+  kPFull = 10,
+  kDpFull = 11,
+  kDsFull = 12,
+  kDqFull = 13,
+  kDqEmpty = 14,
+  kDkvFull = 15,
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+}  // namespace
+
+// =================================================================================================
+// delta = rowsum(O * dO)
+// =================================================================================================
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
+  constexpr int kThreadsPerRow = D / 8;
+  constexpr int kRowsPerBlock = 256 / kThreadsPerRow;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int row = blockIdx.x * kRowsPerBlock + threadIdx.x / kThreadsPerRow;
+  const int part = threadIdx.x % kThreadsPerRow;
+  float acc = 0.f;
+  if (row < p.Sq) {
+    const uint16_t* o = reinterpret_cast<const uint16_t*>(p.o) + batch * p.o_strides[0] + head * p.o_strides[1] +
+                        static_cast<int64_t>(row) * p.o_strides[2] + part * 8;
+    const uint16_t* g = reinterpret_cast<const uint16_t*>(p.dout) + batch * p.do_strides[0] + head * p.do_strides[1] +
+                        static_cast<int64_t>(row) * p.do_strides[2] + part * 8;
+    const uint4 ov = *reinterpret_cast<const uint4*>(o);
+    const uint4 gv = *reinterpret_cast<const uint4*>(g);
+    const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 a, b;
+      if constexpr (kBf16) {
+        a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[i]));
+        b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
+      } else {
+        a = __half22float2(*reinterpret_cast<const __half2*>(&ow[i]));
+        b = __half22float2(*reinterpret_cast<const __half2*>(&gw[i]));
+      }
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+    }
+  }
+#pragma unroll
+  for (int off = kThreadsPerRow / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (part == 0 && row < p.lse_stride)
+    p.delta[(static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + row] = acc;  // padded rows: 0
+}
+
+cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream) {
+  const int rows_per_block = 256 / (p.D / 8);
+  dim3 grid((p.lse_stride + rows_per_block - 1) / rows_per_block, p.Hq, p.B);
+  if (p.D == 128) {
+    if (bf16) fa2_delta_kernel<128, true><<<grid, 256, 0, stream>>>(p);
+    else fa2_delta_kernel<128, false><<<grid, 256, 0, stream>>>(p);
+  } else if (p.D == 64) {
+    if (bf16) fa2_delta_kernel<64, true><<<grid, 256, 0, stream>>>(p);
+    else fa2_delta_kernel<64, false><<<grid, 256, 0, stream>>>(p);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// fused dK / dV / dQ
+// =================================================================================================
+// dQ accumulator layout (opaque workspace, undone by fa2_dq_convert_kernel):
+//   [B][Hq][Sq_pad/128 tiles][D/64 panels][128 rows][64 fp32], and inside a row the 16-byte chunk index is
+//   XOR-ed with (row & 7) so that the staging writes (thread = row) are bank-conflict free.
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+               const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
+               const BwdParams p) {
+  using L = BwdSmem<D>;
+  constexpr int kSub = D / 64;
+  constexpr int kSubBytes = kBlk * 128;  // [128 rows x 64 x 16-bit]
+  constexpr int kPanels = D / 64;
+  constexpr uint32_t kTmemS = 0, kTmemDV = 128, kTmemDK = 256, kTmemDP = 384;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem + L::kKOff;
+  uint8_t* sV = smem + L::kVOff;
+  uint8_t* sQ = smem + L::kQOff;
+  uint8_t* sDO = smem + L::kDOOff;
+  uint8_t* sDS = smem + L::kDsOff;
+  float* sLse = reinterpret_cast<float*>(smem + L::kLseOff);
+  float* sDelta = reinterpret_cast<float*>(smem + L::kDeltaOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_kv_blocks = (p.Sk + kBlk - 1) / kBlk;
+  const int n_q_blocks = (p.Sq + kBlk - 1) / kBlk;
+  const int nblk = n_kv_blocks - 1 - static_cast<int>(blockIdx.x);  // high key blocks are launched first
+  const int head_kv = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int group = p.Hq / p.Hkv;
+  const int shift = p.Sk - p.Sq;
+  const int kv0 = nblk * kBlk;
+
+  // first query block that sees this key block (bottom-right aligned causal mask)
+  int m_start = 0;
+  if (p.causal) m_start = max(0, (kv0 - shift) / kBlk);
+  const int m_count = max(0, n_q_blocks - m_start);
+  const int T = m_count * group;  // iterations: (head in group) x (query block)
+  // Non-causal: key block n starts at query tile n and wraps, so concurrently running CTAs touch different dQ
+  // tiles (and, in deterministic mode, reach each tile in ticket order without a start-up stagger).
+  const bool rotate = !p.causal && (!p.deterministic || (n_kv_blocks <= n_q_blocks && n_kv_blocks <= 128));
+  auto q_block_of = [&](int it) {
+    const int j = it % m_count;
+    return rotate ? (nblk + j) % n_q_blocks : m_start + j;
+  };
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dk);
+    tma_prefetch_desc(&tmap_dv);
+  }
+  if (warp == 12) {
+    if (lane == 0) {
+      mbar_init(&bars[kKvFull], 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bars[kQFull + s], 1);
+        mbar_init(&bars[kQEmpty + s], 1);
+        mbar_init(&bars[kDoFull + s], 1);
+        mbar_init(&bars[kDoEmpty + s], 1);
+      }
+      mbar_init(&bars[kSFull], 1);
+      mbar_init(&bars[kPFull], 256);
+      mbar_init(&bars[kDpFull], 1);
+      mbar_init(&bars[kDsFull], 256);
+      mbar_init(&bars[kDqFull], 1);
+      mbar_init(&bars[kDqEmpty], 128);
+      mbar_init(&bars[kDkvFull], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // setmaxnreg sits at the top of each role's branch: ptxas only widens the register budget for code the
+  // instruction dominates.
+  if (warp >= 12) {
+    reg_dealloc<kRegsIssue>();
+  if (warp == 13) {
+    // ========================================= TMA producer ========================================
+    if (lane == 0 && T > 0) {
+      mbar_arrive_expect_tx(&bars[kKvFull], 2 * L::kTileBytes);
+      for (int j = 0; j < kSub; ++j) {
+        tma_load_4d(sK + j * kSubBytes, &tmap_k, &bars[kKvFull], j * 64, kv0, head_kv, batch);
+        tma_load_4d(sV + j * kSubBytes, &tmap_v, &bars[kKvFull], j * 64, kv0, head_kv, batch);
+      }
+      for (int it = 0; it < T; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int head = head_kv * group + it / m_count;
+        const int m = q_block_of(it);
+        const float* lse_src = p.lse + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
+        const float* delta_src = p.delta + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
+        mbar_wait(&bars[kQEmpty + st], ph ^ 1);
+        mbar_arrive_expect_tx(&bars[kQFull + st], L::kTileBytes + kBlk * 4);
+        for (int j = 0; j < kSub; ++j)
+          tma_load_4d(sQ + st * L::kTileBytes + j * kSubBytes, &tmap_q, &bars[kQFull + st], j * 64, m * kBlk, head, batch);
+        bulk_load_1d(sLse + st * kBlk, lse_src, kBlk * 4, &bars[kQFull + st]);
+        mbar_wait(&bars[kDoEmpty + st], ph ^ 1);
+        mbar_arrive_expect_tx(&bars[kDoFull + st], L::kTileBytes + kBlk * 4);
+        for (int j = 0; j < kSub; ++j)
+          tma_load_4d(sDO + st * L::kTileBytes + j * kSubBytes, &tmap_do, &bars[kDoFull + st], j * 64, m * kBlk, head, batch);
+        bulk_load_1d(sDelta + st * kBlk, delta_src, kBlk * 4, &bars[kDoFull + st]);
+      }
+    }
+  } else if (warp == 12) {
+    // ========================================== MMA issuer =========================================
+    if (lane == 0 && T > 0) {
+      constexpr uint32_t idesc_kk = make_idesc_f16(kBlk, kBlk, kBf16, false, false);  // S^T, dP^T
+      constexpr uint32_t idesc_tn = make_idesc_f16(kBlk, D, kBf16, false, true);      // dV (TS), dK
+      constexpr uint32_t idesc_nn = make_idesc_f16(kBlk, D, kBf16, true, true);       // dQ
+      // K-major views (rows of the tile are the M/N index, reduction runs along the 128-byte rows)
+      const SmemDesc k_kmaj = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const SmemDesc v_kmaj = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+      const SmemDesc q_kmaj = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const SmemDesc do_kmaj = make_smem_desc_sw128(smem_u32(sDO), 16, 1024);
+      const SmemDesc ds_kmaj = make_smem_desc_sw128(smem_u32(sDS), 16, 1024);
+      // MN-major views (rows of the tile are the reduction index)
+      const SmemDesc k_mn = make_smem_desc_sw128(smem_u32(sK), kSubBytes, 1024);
+      const SmemDesc q_mn = make_smem_desc_sw128(smem_u32(sQ), kSubBytes, 1024);
+      const SmemDesc do_mn = make_smem_desc_sw128(smem_u32(sDO), kSubBytes, 1024);
+      const SmemDesc ds_mn = make_smem_desc_sw128(smem_u32(sDS), kSubBytes, 1024);
+
+      // [128 x D] x [128 x D]^T, both K-major, reduction over D
+      auto issue_kmajor = [&](uint32_t d_tmem, SmemDesc a, SmemDesc b) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
+          umma_ss(d_tmem, advance(a, off), advance(b, off), idesc_kk, k > 0 ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(&bars[kKvFull], 0);
+      mbar_wait(&bars[kQFull + 0], 0);
+      tcgen05_fence_after();
+      issue_kmajor(tmem_base + kTmemS, k_kmaj, q_kmaj);
+      umma_commit(&bars[kSFull]);
+
+      for (int it = 0; it < T; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const uint32_t par = it & 1;
+        const uint32_t st_off = st * L::kTileBytes;
+
+        // dV += P^T dO   (A = P^T from TMEM: k-steps 0-3 in columns [0,32), 4-7 in [64,96))
+        mbar_wait(&bars[kPFull], par);
+        mbar_wait(&bars[kDoFull + st], ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < kBlk / 16; ++k) {
+          const uint32_t a_col = (k < 4) ? k * 8 : 64 + (k - 4) * 8;
+          umma_ts(tmem_base + kTmemDV, tmem_base + kTmemS + a_col, advance(do_mn, st_off + k * 2048), idesc_tn,
+                  (it > 0 || k > 0) ? 1u : 0u);
+        }
+        // dP^T = V dO^T  (needs the dP/dQ columns back from the drain warps)
+        if (it > 0) {
+          mbar_wait(&bars[kDqEmpty], (it - 1) & 1);
+          tcgen05_fence_after();
+        }
+        issue_kmajor(tmem_base + kTmemDP, v_kmaj, advance(do_kmaj, st_off));
+        umma_commit(&bars[kDpFull]);
+        if constexpr (!L::kStagingAliasesDO) umma_commit(&bars[kDoEmpty + st]);
+        // S^T(next) = K Q(next)^T
+        if (it + 1 < T) {
+          mbar_wait(&bars[kQFull + (st ^ 1)], ((it + 1) >> 1) & 1);
+          tcgen05_fence_after();
+          issue_kmajor(tmem_base + kTmemS, k_kmaj, advance(q_kmaj, (st ^ 1) * L::kTileBytes));
+          umma_commit(&bars[kSFull]);
+        }
+        // dK += dS^T Q ; dQ = dS K
+        mbar_wait(&bars[kDsFull], par);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < kBlk / 16; ++k) {
+          const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
+          umma_ss(tmem_base + kTmemDK, advance(ds_kmaj, off), advance(q_mn, st_off + k * 2048), idesc_tn,
+                  (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars[kQEmpty + st]);
+#pragma unroll
+        for (int k = 0; k < kBlk / 16; ++k) {
+          umma_ss(tmem_base + kTmemDP, advance(ds_mn, k * 2048), advance(k_mn, k * 2048), idesc_nn, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&bars[kDqFull]);
+      }
+      umma_commit(&bars[kDkvFull]);
+    }
+  }
+  } else if (warp < 8) {
+    // ====================================== compute warpgroups =====================================
+    reg_alloc<kRegsMath>();
+    const int wg = warp >> 2;
+    const int r = threadIdx.x & 127;  // key row inside the block == TMEM lane
+    const int kv = kv0 + r;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + kTmemS + wg * 64;
+    const uint32_t tP = tmem_base + lane_sel + kTmemS + wg * 64;  // P^T (16-bit) over this warpgroup's own S^T columns
+    const uint32_t tDP = tmem_base + lane_sel + kTmemDP + wg * 64;
+    const float c = p.scale_log2;
+
+    for (int it = 0; it < T; ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const uint32_t par = it & 1;
+      const int m = q_block_of(it);
+      const int q0 = m * kBlk + wg * 64;  // first query column of this thread's slice
+      const float* lse_s = sLse + st * kBlk + wg * 64;
+      const float* delta_s = sDelta + st * kBlk + wg * 64;
+      const bool need_mask = (kv0 + kBlk > p.Sk) || (m * kBlk + kBlk > p.Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
+
+      // ---- P^T = exp2(S^T * c - LSE) ----
+      mbar_wait(&bars[kQFull + st], ph);  // LSE slice travels with Q
+      mbar_wait(&bars[kSFull], par);
+      tcgen05_fence_after();
+      uint32_t su[2][32];
+      tmem_ld_32x32b_x32(tS, su[0]);
+      tmem_ld_32x32b_x32(tS + 32, su[1]);
+      tmem_wait_ld();
+      float pf[64];
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + j4 * 4);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = j4 * 4 + e;
+          // lse == -inf marks a fully masked query row: its probabilities are 0, not exp2(+inf)
+          const float neg_lse = (lv[e] == -INFINITY) ? -INFINITY : -lv[e];
+          pf[j] = ex2_approx(fmaf(__uint_as_float(su[j / 32][j % 32]), c, neg_lse));
+        }
+      }
+      if (need_mask) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int qi = q0 + j;
+          const bool ok = (kv < p.Sk) && (qi < p.Sq) && (!p.causal || kv <= qi + shift);
+          pf[j] = ok ? pf[j] : 0.f;
+        }
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[j] = pack2<kBf16>(pf[2 * j], pf[2 * j + 1]);
+        tmem_st_32x32b_x32(tP, pk);
+        tmem_wait_st();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&bars[kPFull]);
+
+      // ---- dS^T = P^T o (dP^T - delta) ----
+      mbar_wait(&bars[kDoFull + st], ph);  // delta slice travels with dO
+      mbar_wait(&bars[kDpFull], par);
+      tcgen05_fence_after();
+      uint8_t* ds_sub = sDS + wg * kSubBytes;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t dpu[32];
+        tmem_ld_32x32b_x32(tDP + half * 32, dpu);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          float ds[8];
+#pragma unroll
+          for (int e4 = 0; e4 < 2; ++e4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(delta_s + half * 32 + c16 * 8 + e4 * 4);
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c16 * 8 + e4 * 4 + e;
+              ds[e4 * 4 + e] = pf[half * 32 + j] * (__uint_as_float(dpu[j]) - dv[e]);
+            }
+          }
+          uint4 v;
+          v.x = pack2<kBf16>(ds[0], ds[1]);
+          v.y = pack2<kBf16>(ds[2], ds[3]);
+          v.z = pack2<kBf16>(ds[4], ds[5]);
+          v.w = pack2<kBf16>(ds[6], ds[7]);
+          *reinterpret_cast<uint4*>(ds_sub + sw128_offset(r, half * 4 + c16)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(&bars[kDsFull]);
+    }
+
+    // ---- epilogue: dK * scale, dV -> smem (the K / V tiles are dead once every MMA retired) -> TMA store ----
+    if (T > 0) {
+      mbar_wait(&bars[kDkvFull], 0);
+      tcgen05_fence_after();
+    }
+    constexpr int kColsPerWg = D / 2;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {  // 0: dK, 1: dV
+      uint8_t* sOut = (which == 0) ? sK : sV;
+      const uint32_t tsrc = tmem_base + lane_sel + (which == 0 ? kTmemDK : kTmemDV) + wg * kColsPerWg;
+      const float mul = (which == 0) ? p.softmax_scale : 1.0f;
+#pragma unroll
+      for (int cidx = 0; cidx < kColsPerWg / 32; ++cidx) {
+        uint32_t o[32];
+        if (T > 0) {
+          tmem_ld_32x32b_x32(tsrc + cidx * 32, o);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+        const int col = wg * kColsPerWg + cidx * 32;  // first head-dim column of this chunk
+        uint8_t* sub = sOut + (col / 64) * kSubBytes;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 v;
+          v.x = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 0]) * mul, __uint_as_float(o[q4 * 8 + 1]) * mul);
+          v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * mul, __uint_as_float(o[q4 * 8 + 3]) * mul);
+          v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * mul, __uint_as_float(o[q4 * 8 + 5]) * mul);
+          v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * mul, __uint_as_float(o[q4 * 8 + 7]) * mul);
+          *reinterpret_cast<uint4*>(sub + sw128_offset(r, ((col % 64) / 8) + q4)) = v;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 256);
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < kSub; ++j) {
+        tma_store_4d(&tmap_dk, sK + j * kSubBytes, j * 64, kv0, head_kv, batch);
+        tma_store_4d(&tmap_dv, sV + j * kSubBytes, j * 64, kv0, head_kv, batch);
+      }
+      bulk_commit_group();
+      bulk_wait_group_read<0>();
+    }
+  } else {
+    // ========================================== dQ drain ===========================================
+    reg_alloc<kRegsMath>();
+    const int r = threadIdx.x & 127;  // query row inside the block == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tDQ = tmem_base + lane_sel + kTmemDP;
+    const bool leader = (r == 0);
+
+    for (int it = 0; it < T; ++it) {
+      const int st = it & 1;
+      const uint32_t par = it & 1;
+      const int head = head_kv * group + it / m_count;
+      const int m = q_block_of(it);
+      uint8_t* stage = L::kStagingAliasesDO ? (sDO + st * L::kTileBytes) : (smem + L::kStageOff);
+      float* gtile = p.dq_accum + ((static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / kBlk) + m) *
+                                      static_cast<int64_t>(kBlk) * D;
+
+      mbar_wait(&bars[kDqFull], par);
+      tcgen05_fence_after();
+      uint32_t acc[kPanels][2][32];
+#pragma unroll
+      for (int pn = 0; pn < kPanels; ++pn) {
+        tmem_ld_32x32b_x32(tDQ + pn * 64, acc[pn][0]);
+        tmem_ld_32x32b_x32(tDQ + pn * 64 + 32, acc[pn][1]);
+      }
+      tmem_wait_ld();
+      tcgen05_fence_before();
+      mbar_arrive(&bars[kDqEmpty]);  // dP^T(next) may overwrite these columns now
+
+      int* ticket = nullptr;
+      int my_turn = 0;
+      if (p.deterministic) {
+        ticket = p.dq_sem + (static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / kBlk) + m;
+        if (p.causal) {
+          // key blocks visible to query tile m: 0 .. n_last; they add in descending order
+          const int last_row = min(m * kBlk + kBlk, p.Sq) - 1;
+          const int n_last = min(n_kv_blocks - 1, (last_row + shift) / kBlk);
+          my_turn = n_last - nblk;
+        } else if (rotate) {
+          // rotated schedule: key block n reaches query tile m at step (m - n) mod n_q_blocks
+          const int top = min(m, n_kv_blocks - 1);
+          my_turn = (nblk <= m) ? (top - nblk) : (top + 1 + (n_kv_blocks - 1 - nblk));
+        } else {
+          my_turn = n_kv_blocks - 1 - nblk;
+        }
+      }
+
+#pragma unroll
+      for (int pn = 0; pn < kPanels; ++pn) {
+        // staging must be free of the previous bulk reduction's reads
+        if (pn > 0 || !L::kStagingAliasesDO) {
+          if (leader) bulk_wait_group_read<0>();
+          named_bar_sync(2, 128);
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            uint4 v;
+            v.x = acc[pn][h2][c4 * 4 + 0];
+            v.y = acc[pn][h2][c4 * 4 + 1];
+            v.z = acc[pn][h2][c4 * 4 + 2];
+            v.w = acc[pn][h2][c4 * 4 + 3];
+            const uint32_t chunk = h2 * 8 + c4;  // 16-byte chunk inside the 256-byte row
+            *reinterpret_cast<uint4*>(stage + r * 256 + ((chunk ^ (r & 7)) << 4)) = v;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (leader) {
+          if (p.deterministic && pn == 0) {
+            const long long start = clock64();
+            while (ld_acquire(ticket) != my_turn) {
+              if (clock64() - start > FA2_WATCHDOG_CYCLES) __trap();
+            }
+          }
+          bulk_reduce_add_f32(gtile + pn * (kBlk * 64), stage, L::kPanelBytes);
+          bulk_commit_group();
+        }
+      }
+      if (leader) {
+        if (p.deterministic) {
+          bulk_wait_group<0>();
+          __threadfence();
+          st_release(ticket, my_turn + 1);
+        } else {
+          bulk_wait_group_read<0>();
+        }
+        if constexpr (L::kStagingAliasesDO) mbar_arrive(&bars[kDoEmpty + st]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D, bool kBf16>
+static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
+                                const BwdParams& p, cudaStream_t stream) {
+  auto kernel = fa2_bwd_kernel<D, kBf16>;
+  constexpr int smem = BwdSmem<D>::kBytes;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv, p.B);
+  kernel<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p,
+                       cudaStream_t stream) {
+  if (D == 128) return bf16 ? launch_bwd_t<128, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)
+                            : launch_bwd_t<128, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
+  if (D == 64) return bf16 ? launch_bwd_t<64, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)
+                           : launch_bwd_t<64, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
+  return cudaErrorInvalidValue;
+}
+
+// =================================================================================================
+// dQ accumulator -> dQ
+// =================================================================================================
+__global__ void __launch_bounds__(256) fa2_dq_convert_kernel(const DqConvertParams p) {
+  // one thread per 16-byte chunk (4 floats) of the accumulator
+  const int chunks_per_row = p.D / 4;
+  const int64_t total = static_cast<int64_t>(p.B) * p.Hq * p.Sq * chunks_per_row;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cd = static_cast<int>(idx % chunks_per_row);  // logical chunk along D
+    int64_t rest = idx / chunks_per_row;
+    const int head = static_cast<int>(rest % p.Hq);
+    rest /= p.Hq;
+    const int row = static_cast<int>(rest % p.Sq);
+    const int batch = static_cast<int>(rest / p.Sq);
+    const int tile = row / 128, r = row % 128;
+    const int panel = cd / 16, chunk = cd % 16;
+    const int64_t tile_base = ((static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / 128) + tile) * 128LL * p.D;
+    const float* src = p.dq_accum + tile_base + static_cast<int64_t>(panel) * (128 * 64) + r * 64 + ((chunk ^ (r & 7)) << 2);
+    float4 v = *reinterpret_cast<const float4*>(src);
+    v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
+    const int64_t dst = batch * p.dq_strides[0] + head * p.dq_strides[1] + static_cast<int64_t>(row) * p.dq_strides[2] + cd * 4;
+    if (p.out_dtype == 32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dq) + dst) = v;
+    } else if (p.out_dtype == 17) {
+      uint2 o;
+      o.x = pack2<true>(v.x, v.y);
+      o.y = pack2<true>(v.z, v.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dq) + dst) = o;
+    } else {
+      uint2 o;
+      o.x = pack2<false>(v.x, v.y);
+      o.y = pack2<false>(v.z, v.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dq) + dst) = o;
+    }
+  }
+}
+
+cudaError_t launch_dq_convert(const DqConvertParams& p, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(p.B) * p.Hq * p.Sq * (p.D / 4);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fa2_dq_convert_kernel<<<blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace fa2

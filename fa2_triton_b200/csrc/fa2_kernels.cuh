@@ -1,0 +1,84 @@
+// Internal interface between the C-ABI translation unit (api.cu) and the kernel translation units.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fa2 {
+
+// ---------------------------------------------------------------------------------------------
+// forward (fwd_sm100.cu)
+// ---------------------------------------------------------------------------------------------
+struct FwdParams {
+  float* lse;        // [B, Hq, lse_stride] fp32, log2 domain
+  int B, Hq, Hkv, Sq, Sk;
+  int lse_stride;    // ceil(Sq / 128) * 128
+  float scale_log2;  // softmax_scale * log2(e)
+  int causal;
+  int n_pairs;       // ceil(Sq / 256): one CTA per pair of 128-row query tiles
+};
+
+cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const CUtensorMap& to, const FwdParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// backward (bwd_sm100.cu)
+// ---------------------------------------------------------------------------------------------
+struct DeltaParams {
+  const void* o;
+  const void* dout;
+  float* delta;  // [B, Hq, lse_stride]
+  int B, Hq, Sq, D;
+  int lse_stride;
+  int64_t o_strides[3];   // batch, head, seq (elements)
+  int64_t do_strides[3];
+};
+cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream);
+
+struct BwdParams {
+  const float* lse;    // [B, Hq, lse_stride] log2 domain
+  const float* delta;  // [B, Hq, lse_stride]
+  float* dq_accum;     // [B, Hq, Sq_pad, D] fp32, tile-swizzled (see bwd_sm100.cu)
+  int* dq_sem;         // [B, Hq, Sq_pad/128] ordered-reduction tickets (deterministic mode) or nullptr
+  int B, Hq, Hkv, Sq, Sk;
+  int lse_stride;
+  int sq_pad;  // ceil(Sq / 128) * 128
+  float softmax_scale;
+  float scale_log2;
+  int causal;
+  int deterministic;
+};
+cudaError_t launch_bwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p,
+                       cudaStream_t stream);
+
+struct DqConvertParams {
+  const float* dq_accum;  // as written by the backward kernel
+  void* dq;               // [B, Sq, Hq, D] with strides below
+  int B, Hq, Sq, D;
+  int sq_pad;
+  int64_t dq_strides[3];  // batch, head, seq (elements)
+  float scale;            // softmax_scale (dS is accumulated unscaled)
+  int out_dtype;          // 16 = fp16, 17 = bf16, 32 = fp32
+};
+cudaError_t launch_dq_convert(const DqConvertParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// UMMA / TMA probe (probe_sm100.cu): one 128 x N x K tile product through every operand path
+// the attention kernels use. Test infrastructure for tests/test_umma_probe.py.
+// ---------------------------------------------------------------------------------------------
+struct ProbeParams {
+  const void* a;  // 16-bit, layout depends on a_mode
+  const void* b;  // 16-bit, layout depends on b_mode
+  float* d;       // [128, N] fp32 row-major
+  int N;          // 64 or 128
+  int K;          // 64 or 128
+  int a_mode;     // 0: smem K-major via TMA ([128,K] row-major)   1: smem MN-major, written by threads ([K,128] row-major)
+                  // 2: TMEM (threads pack 16-bit pairs, tcgen05.st)  ([128,K] row-major)
+  int b_mode;     // 0: smem K-major via TMA ([N,K] row-major)     1: smem MN-major via TMA ([K,N] row-major)
+};
+cudaError_t launch_probe(bool bf16, const CUtensorMap& ta, const CUtensorMap& tb, const ProbeParams& p,
+                         cudaStream_t stream);
+
+}  // namespace fa2

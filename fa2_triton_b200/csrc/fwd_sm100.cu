@@ -1,0 +1,390 @@
+// FlashAttention-2 forward for sm_100a (B200): TMA -> smem ring -> tcgen05.mma (S = Q K^T, O += P V) with
+// accumulators in tensor memory, two 128-row Q tiles per CTA whose softmax warpgroups ping-pong against
+// the single MMA-issuing warp.
+//
+// Replaces the reference's `_fwd_kernel` (src/forward/kernel.py:61-291) + `compute_row_block`
+// (src/forward/compute_row_blocks.py:8-103). Same arithmetic contract:
+//   S = Q K^T (fp32 acc); masked where col >= Sk or (causal) col > row + Sk - Sq;
+//   log2-domain online softmax with c = softmax_scale * log2(e); P rounded to the input dtype before PV;
+//   O = (P V) / l in the input dtype;  LSE2 = m + log2(l) in fp32 (src/forward/kernel.py:119,259-272).
+//
+// CTA = 12 warps:
+//   warps 0-3  : softmax warpgroup for Q tile 0 (one thread per query row; TMEM lane == row)
+//   warps 4-7  : softmax warpgroup for Q tile 1
+//   warp  8    : MMA issuer (one elected lane)           warp 9 : TMA producer (one elected lane)
+//   warps 10-11: idle (keep the third warpgroup whole for setmaxnreg)
+// TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,256+D) | O1 [256+D,256+2D).
+//   P_t (16-bit, 64 columns) overwrites the first half of S_t once the owning thread has read its row.
+#include "fa2_kernels.cuh"
+#include "ptx.cuh"
+
+namespace fa2 {
+
+namespace {
+
+constexpr int kBM = 128;  // query rows per tile (= TMEM lanes)
+constexpr int kBN = 128;  // key rows per block
+constexpr int kFwdThreads = 384;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between rescales
+
+template <int D>
+struct FwdSmem {
+  static constexpr int kStages = (D == 128) ? 2 : 4;
+  static constexpr int kTileBytes = kBM * D * 2;  // Q, K and V tiles all have 128 rows
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = kQOff + 2 * kTileBytes;
+  static constexpr int kVOff = kKOff + kStages * kTileBytes;
+  static constexpr int kBarOff = kVOff + kStages * kTileBytes;
+  // barriers: q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full[2]
+  static constexpr int kNumBars = 1 + 4 * kStages + 6;
+  static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
+  static constexpr int kBytes = kTmemSlotOff + 16;
+  static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-byte alignment
+};
+
+// number of key blocks query tile [row0, row0+128) has to visit
+__device__ __forceinline__ int num_kv_blocks(int row0, int Sq, int Sk, int causal) {
+  if (row0 >= Sq) return 0;
+  int last_row = min(row0 + kBM, Sq) - 1;
+  int cols = causal ? min(Sk, last_row + Sk - Sq + 1) : Sk;
+  return cols <= 0 ? 0 : (cols + kBN - 1) / kBN;
+}
+
+}  // namespace
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+               const FwdParams p) {
+  using L = FwdSmem<D>;
+  constexpr int kStages = L::kStages;
+  constexpr int kSub = D / 64;           // 64-column (128-byte) sub-tiles per row
+  constexpr int kSubBytes = kBM * 128;   // one [128 x 64] 16-bit sub-tile
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + L::kQOff;
+  uint8_t* sK = smem + L::kKOff;
+  uint8_t* sV = smem + L::kVOff;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kStages;
+  uint64_t* v_full = k_empty + kStages;
+  uint64_t* v_empty = v_full + kStages;
+  uint64_t* s_full = v_empty + kStages;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // heaviest (largest row index) tile pairs first: better tail behaviour under causal masking
+  const int pair = p.n_pairs - 1 - static_cast<int>(blockIdx.x);
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int head_kv = head / (p.Hq / p.Hkv);
+  const int row0 = pair * 2 * kBM;
+
+  const int nblk0 = num_kv_blocks(row0, p.Sq, p.Sk, p.causal);
+  const int nblk1 = num_kv_blocks(row0 + kBM, p.Sq, p.Sk, p.causal);
+  const int nblk_max = max(nblk0, nblk1);
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+      }
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(&s_full[t], 1);
+        mbar_init(&p_full[t], kBM);
+        mbar_init(&o_full[t], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // setmaxnreg at the top of each role branch (ptxas widens the budget only for dominated code):
+  // 2 softmax warpgroups x 128 x 208 + 1 issue warpgroup x 128 x 96 = 65536 registers
+  if (warp >= 8) {
+    reg_dealloc<96>();
+  if (warp == 9) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0 && nblk_max > 0) {
+      const int n_q_tiles = (row0 + kBM < p.Sq) ? 2 : 1;
+      mbar_arrive_expect_tx(q_full, n_q_tiles * L::kTileBytes);
+      for (int t = 0; t < n_q_tiles; ++t)
+        for (int j = 0; j < kSub; ++j)
+          tma_load_4d(sQ + t * L::kTileBytes + j * kSubBytes, &tmap_q, q_full, j * 64, row0 + t * kBM, head, batch);
+      for (int i = 0; i < nblk_max; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], L::kTileBytes);
+        for (int j = 0; j < kSub; ++j)
+          tma_load_4d(sK + s * L::kTileBytes + j * kSubBytes, &tmap_k, &k_full[s], j * 64, i * kBN, head_kv, batch);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], L::kTileBytes);
+        for (int j = 0; j < kSub; ++j)
+          tma_load_4d(sV + s * L::kTileBytes + j * kSubBytes, &tmap_v, &v_full[s], j * 64, i * kBN, head_kv, batch);
+      }
+    }
+  } else if (warp == 8) {
+    // ======================================== MMA issuer ========================================
+    if (lane == 0 && nblk_max > 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kBM, kBN, kBf16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(kBM, D, kBf16, false, true);
+      const int nblk[2] = {nblk0, nblk1};
+
+      const SmemDesc q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);       // K-major
+      const SmemDesc k_desc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);       // K-major
+      const SmemDesc v_desc = make_smem_desc_sw128(smem_u32(sV), kSubBytes, 1024);  // MN-major
+      auto issue_qk = [&](int t, int stage) {
+        const SmemDesc qa = advance(q_desc, t * L::kTileBytes);
+        const SmemDesc ka = advance(k_desc, stage * L::kTileBytes);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
+          umma_ss(tmem_base + t * kBN, advance(qa, off), advance(ka, off), idesc_qk, k > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int stage, bool accumulate) {
+        const SmemDesc va = advance(v_desc, stage * L::kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBN / 16; ++k) {
+          umma_ts(tmem_base + 256 + t * D, tmem_base + t * kBN + k * 8, advance(va, k * 2048), idesc_pv,
+                  (accumulate || k > 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tcgen05_fence_after();
+      for (int t = 0; t < 2; ++t) {
+        if (nblk[t] > 0) {
+          issue_qk(t, 0);
+          umma_commit(&s_full[t]);
+        }
+      }
+      umma_commit(&k_empty[0]);
+
+      for (int i = 0; i < nblk_max; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        const int sn = (i + 1) % kStages;
+        const uint32_t phn = ((i + 1) / kStages) & 1;
+        bool next_k_ready = false;
+        mbar_wait(&v_full[s], ph);
+        for (int t = 0; t < 2; ++t) {
+          if (i >= nblk[t]) continue;
+          mbar_wait(&p_full[t], i & 1);
+          tcgen05_fence_after();
+          issue_pv(t, s, i > 0);
+          if (i + 1 < nblk[t]) {
+            if (!next_k_ready) {
+              mbar_wait(&k_full[sn], phn);
+              tcgen05_fence_after();
+              next_k_ready = true;
+            }
+            issue_qk(t, sn);
+            umma_commit(&s_full[t]);
+          } else {
+            umma_commit(&o_full[t]);
+          }
+        }
+        umma_commit(&v_empty[s]);
+        if (i + 1 < nblk_max) umma_commit(&k_empty[sn]);
+      }
+    }
+  }
+  } else {
+    // ===================================== softmax warpgroups ====================================
+    reg_alloc<208>();
+    const int t = warp >> 2;
+    const int r = threadIdx.x & 127;  // row inside the tile == TMEM lane
+    const int tile_row0 = row0 + t * kBM;
+    const int row = tile_row0 + r;
+    const int nblk = t == 0 ? nblk0 : nblk1;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + t * kBN;
+    const uint32_t tO = tmem_base + lane_sel + 256 + t * D;
+    const float c = p.scale_log2;
+    const int shift = p.Sk - p.Sq;
+
+    float m_ref = -INFINITY;
+    float l = 0.f;
+
+    for (int i = 0; i < nblk; ++i) {
+      mbar_wait(&s_full[t], i & 1);
+      tcgen05_fence_after();
+
+      uint32_t su[kBN / 32][32];  // raw fp32 bits of this thread's score row
+#pragma unroll
+      for (int cidx = 0; cidx < kBN / 32; ++cidx) tmem_ld_32x32b_x32(tS + cidx * 32, su[cidx]);
+      tmem_wait_ld();
+      float s[kBN];
+#pragma unroll
+      for (int j = 0; j < kBN; ++j) s[j] = __uint_as_float(su[j / 32][j % 32]);
+
+      const int col0 = i * kBN;
+      const int block_last = col0 + kBN - 1;
+      const bool need_mask = (block_last >= p.Sk) || (p.causal && block_last > tile_row0 + shift);
+      if (need_mask) {
+        const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
+#pragma unroll
+        for (int j = 0; j < kBN; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
+      }
+
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int j = 4; j < kBN; j += 4) {
+        mx0 = fmaxf(mx0, s[j]);
+        mx1 = fmaxf(mx1, s[j + 1]);
+        mx2 = fmaxf(mx2, s[j + 2]);
+        mx3 = fmaxf(mx3, s[j + 3]);
+      }
+      const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+
+      // lazy rescale: only move the reference max when the block max exceeds it by > 2^8
+      const bool need = mb > m_ref + kRescaleThreshold;
+      float alpha = 1.f;
+      if (need) {
+        alpha = ex2_approx(m_ref - mb);  // m_ref == -inf -> 0
+        m_ref = mb;
+      }
+      if (i > 0 && __any_sync(0xffffffffu, need)) {
+#pragma unroll
+        for (int cidx = 0; cidx < D / 32; ++cidx) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tO + cidx * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          tmem_st_32x32b_x32(tO + cidx * 32, o);
+        }
+      }
+      l *= alpha;
+
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t pk[kBN / 64][32];
+#pragma unroll
+      for (int j = 0; j < kBN; j += 2) {
+        const float p0 = ex2_approx(fmaf(s[j], c, neg_m));
+        const float p1 = ex2_approx(fmaf(s[j + 1], c, neg_m));
+        l0 += p0;
+        l1 += p1;
+        pk[j / 64][(j / 2) % 32] = pack2<kBf16>(p0, p1);
+      }
+      l += l0 + l1;
+#pragma unroll
+      for (int cidx = 0; cidx < kBN / 64; ++cidx) tmem_st_32x32b_x32(tS + cidx * 32, pk[cidx]);
+      tmem_wait_st();
+      tcgen05_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    // ------------------------------ epilogue: O / l -> smem -> TMA store ---------------------------
+    if (tile_row0 < p.Sq) {
+      const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+      if (nblk > 0) {
+        mbar_wait(&o_full[t], 0);
+        tcgen05_fence_after();
+      }
+      uint8_t* sO = sQ + t * L::kTileBytes;  // the Q tile is dead once o_full fired
+#pragma unroll
+      for (int cidx = 0; cidx < D / 32; ++cidx) {
+        uint32_t o[32];
+        if (nblk > 0) {
+          tmem_ld_32x32b_x32(tO + cidx * 32, o);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+        uint8_t* sub = sO + (cidx / 2) * kSubBytes;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 v;
+          v.x = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
+          v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
+          v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
+          v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
+          const uint32_t chunk16 = (cidx % 2) * 4 + q4;
+          *reinterpret_cast<uint4*>(sub + sw128_offset(r, chunk16)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, kBM);
+      if (r == 0) {
+        for (int j = 0; j < kSub; ++j) tma_store_4d(&tmap_o, sO + j * kSubBytes, j * 64, tile_row0, head, batch);
+        bulk_commit_group();
+        bulk_wait_group_read<0>();
+      }
+      // LSE (log2 domain), padded rows get 0
+      float* lse_row = p.lse + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride;
+      if (row < p.lse_stride) {
+        float lse = 0.f;
+        if (row < p.Sq) lse = (l > 0.f) ? m_ref + lg2_approx(l) : -INFINITY;
+        lse_row[row] = lse;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+template <int D, bool kBf16>
+static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
+  auto kernel = fa2_fwd_kernel<D, kBf16>;
+  constexpr int smem = FwdSmem<D>::kDynBytes;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  dim3 grid(p.n_pairs, p.Hq, p.B);
+  kernel<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
+  if (D == 128) return bf16 ? launch_fwd_t<128, true>(tq, tk, tv, to, p, stream)
+                            : launch_fwd_t<128, false>(tq, tk, tv, to, p, stream);
+  if (D == 64) return bf16 ? launch_fwd_t<64, true>(tq, tk, tv, to, p, stream)
+                           : launch_fwd_t<64, false>(tq, tk, tv, to, p, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace fa2

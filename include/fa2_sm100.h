@@ -1,0 +1,105 @@
+/*
+ * fa2_sm100.h - C ABI of libfa2_sm100.so: FlashAttention-2 forward / backward for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of remi-or/fa2_triton. Each entry point replaces one
+ * Triton launch site of the reference (paths relative to the reference repository):
+ *
+ *   fa2_sm100_fwd            <- `_fwd_kernel[grid](...)`       src/forward/caller.py:83-116
+ *   fa2_sm100_bwd_delta      <- `_compute_delta[grid](...)`    src/backward/caller.py:94-114
+ *   fa2_sm100_bwd            <- `_bwd_kernel[grid](...)`       src/backward/caller.py:118-160
+ *   fa2_sm100_dq_convert     <- the fp32 `dq` the reference allocates at src/backward/caller.py:86
+ *                               (our dQ accumulator is an opaque tile-swizzled workspace; this call turns it
+ *                               into the caller-visible [B, Sq, Hq, D] tensor)
+ *
+ * Conventions shared by every call
+ *   - tensors are device pointers; q/o/do are [B, Sq, Hq, D], k/v/dk/dv are [B, Sk, Hkv, D] with a contiguous
+ *     last dimension; `*_strides[3]` are the (batch, head, seq) strides in ELEMENTS - the same triple the
+ *     reference passes as `x.stride(0), x.stride(2), x.stride(1)` (src/forward/caller.py:93-96)
+ *   - `dtype` uses the reference's autotune-key encoding (src/utils.py:102-109): 16 = float16, 17 = bfloat16
+ *   - lse / delta are fp32 [B, Hq, lse_row_stride] with lse_row_stride = ceil(Sq / 128) * 128
+ *     (src/forward/caller.py:73-74); LSE is in the log2 domain: m + log2(l) with scores pre-multiplied by
+ *     softmax_scale * log2(e) (src/forward/kernel.py:119)
+ *   - causal masking is bottom-right aligned: key j is visible to query i iff j <= i + Sk - Sq
+ *     (src/forward/compute_row_blocks.py:64-66)
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no allocation, no sync)
+ *   - return value: 0 on success; > 0 a cudaError_t / CUresult from the driver; < 0 an FA2_E_* argument error.
+ *     fa2_sm100_last_error() returns a thread-local description of the last failure.
+ *   - thread safety: calls may be made concurrently from different host threads.
+ *
+ * Supported in this build: D in {64, 128}; Hq % Hkv == 0; any Sq, Sk >= 1; base pointers 16-byte aligned and
+ * every stride a multiple of 8 elements (TMA requirement).
+ */
+#ifndef FA2_SM100_H_
+#define FA2_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA2_SM100_ABI_VERSION 1
+
+#define FA2_DTYPE_FP16 16
+#define FA2_DTYPE_BF16 17
+#define FA2_DTYPE_FP32 32
+
+#define FA2_E_UNSUPPORTED_HEAD_DIM (-1)
+#define FA2_E_UNSUPPORTED_DTYPE (-2)
+#define FA2_E_BAD_SHAPE (-3)
+#define FA2_E_BAD_ALIGNMENT (-4)
+#define FA2_E_NULL_POINTER (-5)
+#define FA2_E_WORKSPACE_TOO_SMALL (-6)
+#define FA2_E_NO_DRIVER (-7)
+
+int fa2_sm100_version(void);
+const char* fa2_sm100_last_error(void);
+
+/* O = softmax(Q K^T * softmax_scale [+ causal mask]) V and the log2-domain LSE. */
+int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                  int B, int Hq, int Hkv, int Sq, int Sk, int D,
+                  const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                  const int64_t o_strides[3], int64_t lse_row_stride,
+                  float softmax_scale, int causal, int dtype, void* stream);
+
+/* delta[b, h, i] = sum_d O[b, i, h, d] * dO[b, i, h, d] in fp32; rows in [Sq, lse_row_stride) are set to 0. */
+int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
+                        int B, int Hq, int Sq, int D,
+                        const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride,
+                        int dtype, void* stream);
+
+/* Bytes of scratch fa2_sm100_bwd needs: the fp32 dQ accumulator plus (deterministic mode) one int per
+ * (batch, head, 128-row query tile). The workspace must be 16-byte aligned. */
+size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic);
+
+/* dK, dV (input dtype, [B, Sk, Hkv, D]) and the fp32 dQ accumulator inside `workspace`.
+ * The call zero-fills what it needs of the workspace itself (cudaMemsetAsync on `stream`).
+ * deterministic != 0: contributions to each dQ tile are added in a fixed key-block order, results are
+ * bit-identical run to run; deterministic == 0: same adds in arrival order (fast mode). */
+int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
+                  const float* lse, const float* delta,
+                  void* dk, void* dv, void* workspace, size_t workspace_bytes,
+                  int B, int Hq, int Hkv, int Sq, int Sk, int D,
+                  const int64_t do_strides[3], const int64_t q_strides[3], const int64_t k_strides[3],
+                  const int64_t v_strides[3], const int64_t dk_strides[3], const int64_t dv_strides[3],
+                  int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype,
+                  void* stream);
+
+/* dq[b, i, h, :] = softmax_scale * accumulator[b, h, i, :], written as `out_dtype` (16, 17 or 32). */
+int fa2_sm100_dq_convert(const void* workspace, void* dq,
+                         int B, int Hq, int Sq, int D,
+                         const int64_t dq_strides[3], float softmax_scale, int out_dtype, void* stream);
+
+/* Hardware probe used by the test-suite: D[128, N] = A * B through one UMMA operand path.
+ * a_mode 0: A [128, K] row-major (smem, K-major)   1: A given transposed [K, 128] (smem, MN-major)
+ *        2: A [128, K] row-major staged in tensor memory
+ * b_mode 0: B given as [N, K] row-major (K-major)  1: B given as [K, N] row-major (MN-major) */
+int fa2_sm100_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_mode, int b_mode,
+                               int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FA2_SM100_H_ */

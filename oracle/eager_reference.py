@@ -1,0 +1,70 @@
+"""Eager-PyTorch port of the reference's CPU path. TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+``flash_attn_reference`` restates src/reference_implementation.py:38-123 for the arguments the hot path uses
+(q, k, v, causal, upcast, reorder_ops): einsum scores -> -inf masking -> softmax -> einsum with V, gradients by
+PyTorch autograd. It is the thing ``bench.py`` times as the CPU baseline (kind "port") and the "low precision
+PyTorch" arm of the reference's error criterion (tests/utils.py:68-142). It is validated against the numpy
+oracle and the golden vectors in tests/test_oracle.py.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def flash_attn_reference(q, k, v, causal=False, upcast=True, reorder_ops=False, softmax_scale=None):
+    """q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] -> output [B,Sq,Hq,D] in q's dtype.
+
+    upcast: compute in fp32 (src/reference_implementation.py:77-78). reorder_ops: scale K instead of Q
+    (:83-86), used by the reference tests to estimate the error of a same-precision implementation.
+    """
+    out_dtype = q.dtype
+    if upcast:
+        q, k, v = q.float(), k.float(), v.float()
+    sq, sk = q.shape[1], k.shape[1]
+    group = q.shape[2] // k.shape[2]
+    if group > 1:  # :80-81
+        k = k.repeat_interleave(group, dim=2)
+        v = v.repeat_interleave(group, dim=2)
+    scale = 1.0 / math.sqrt(q.shape[-1]) if softmax_scale is None else softmax_scale
+    if reorder_ops:
+        scores = torch.einsum("bthd,bshd->bhts", q, k * scale)
+    else:
+        scores = torch.einsum("bthd,bshd->bhts", q * scale, k)
+    hidden = None
+    if causal:  # :8-29 with window (-1, 0): bottom-right aligned
+        row = torch.arange(sq, device=q.device).unsqueeze(-1)
+        col = torch.arange(sk, device=q.device)
+        hidden = col > row + (sk - sq)
+        scores = scores.masked_fill(hidden, float("-inf"))
+    attn = torch.softmax(scores, dim=-1).to(v.dtype)  # :105
+    if hidden is not None:  # rows without any visible key: 0 instead of NaN (:107-108)
+        attn = attn.masked_fill(torch.all(hidden, dim=-1, keepdim=True), 0.0)
+    out = torch.einsum("bhts,bshd->bthd", attn, v)  # :120
+    return out.to(out_dtype)
+
+
+def fwd_bwd(q, k, v, do, causal=False, upcast=True, reorder_ops=False):
+    """Forward + autograd backward: (out, dq, dk, dv). Inputs are left untouched."""
+    q, k, v = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    out = flash_attn_reference(q, k, v, causal=causal, upcast=upcast, reorder_ops=reorder_ops)
+    dq, dk, dv = torch.autograd.grad(out, (q, k, v), do)
+    return out.detach(), dq, dk, dv
+
+
+def lse_log2(q, k, causal=False, softmax_scale=None):
+    """fp32 log2-domain logsumexp [B, Hq, Sq] - the quantity the forward kernel saves
+    (src/forward/kernel.py:119; tests/test_logsumexp.py:53-74 states the same definition)."""
+    q, k = q.float(), k.float()
+    sq, sk = q.shape[1], k.shape[1]
+    group = q.shape[2] // k.shape[2]
+    if group > 1:
+        k = k.repeat_interleave(group, dim=2)
+    scale = 1.0 / math.sqrt(q.shape[-1]) if softmax_scale is None else softmax_scale
+    scores = torch.einsum("bthd,bshd->bhts", q, k) * scale
+    if causal:
+        row = torch.arange(sq, device=q.device).unsqueeze(-1)
+        col = torch.arange(sk, device=q.device)
+        scores = scores.masked_fill(col > row + (sk - sq), float("-inf"))
+    return torch.logsumexp(scores, dim=-1) * 1.4426950408889634

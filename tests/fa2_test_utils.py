@@ -1,0 +1,50 @@
+"""Shared helpers for the parity tests (our restatement of the reference's tests/utils.py + tests/core.py)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import torch
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+# north-star tolerances (BASELINE.json): bf16 tensors |x - ref| <= 2e-2 + 1e-2 * |ref|, LSE abs 1e-3
+ATOL_16, RTOL_16 = 2e-2, 1e-2
+ATOL_LSE = 1e-3
+
+
+def generate_test_data(B, Sq, Sk, Hq, Hkv, D, dtype, device, seed=0):
+    """Same recipe as the reference's tests/utils.py:9-26: seed, Q/K/V ~ N(0, 0.5^2), dO ~ N(0, 1)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    q = torch.empty(B, Sq, Hq, D, dtype=torch.float32).normal_(0, 0.5, generator=g)
+    k = torch.empty(B, Sk, Hkv, D, dtype=torch.float32).normal_(0, 0.5, generator=g)
+    v = torch.empty(B, Sk, Hkv, D, dtype=torch.float32).normal_(0, 0.5, generator=g)
+    do = torch.empty(B, Sq, Hq, D, dtype=torch.float32).normal_(0, 1.0, generator=g)
+    return tuple(t.to(dtype).to(device) for t in (q, k, v, do))
+
+
+def assert_close_16(name, got, ref, atol=ATOL_16, rtol=RTOL_16):
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(got).all(), f"{name}: non-finite values"
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    worst = (err - bound).max().item()
+    assert worst <= 0, f"{name}: max |err| {err.max().item():.4e}, exceeds atol+rtol*|ref| by {worst:.4e}"
+
+
+def assert_reference_criterion(name, got, ref_fp32, ref_lowp, mult, atol):
+    """The reference's own acceptance test (tests/utils.py:93,126-140): our error against the fp32 oracle must be
+    within `mult` x the error of the same-precision eager PyTorch computation (+ atol)."""
+    e_ours = (got.float() - ref_fp32.float()).abs().max().item()
+    e_pt = (ref_lowp.float() - ref_fp32.float()).abs().max().item()
+    assert e_ours <= mult * e_pt + atol, f"{name}: ours {e_ours:.4e} > {mult} * pytorch {e_pt:.4e} + {atol}"
+
+
+def load_golden(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    return {k: z[k] for k in z.files}
+
+
+def golden_names():
+    return sorted(p.stem for p in GOLDEN.glob("*.npz"))

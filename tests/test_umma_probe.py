@@ -1,0 +1,30 @@
+"""GPU: pin the UMMA descriptor encodings (ptx.cuh) against a torch matmul, one operand path at a time."""
+import pytest
+import torch
+
+from fa2_triton_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+MODES = [(0, 0), (0, 1), (2, 1), (2, 0), (1, 1), (1, 0)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,k", [(128, 128), (64, 128), (128, 64), (64, 64)])
+@pytest.mark.parametrize("a_mode,b_mode", MODES)
+def test_probe_matches_matmul(a_mode, b_mode, n, k, dtype):
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(a_mode * 10 + b_mode)
+    a = torch.randn(128, k, generator=g).to(dtype).to(dev)   # logical A [M=128, K]
+    b = torch.randn(k, n, generator=g).to(dtype).to(dev)     # logical B [K, N]
+    ref = a.float() @ b.float()
+    a_arg = a.t().contiguous() if a_mode == 1 else a.contiguous()  # mode 1 takes A^T [K, 128]
+    b_arg = b.t().contiguous() if b_mode == 0 else b.contiguous()  # mode 0 takes B^T [N, K]
+    d = torch.full((128, n), float("nan"), device=dev, dtype=torch.float32)
+    code = lib.fa2_sm100_debug_umma_probe(a_arg.data_ptr(), b_arg.data_ptr(), d.data_ptr(), n, k, a_mode, b_mode,
+                                          _lib.DTYPE_BF16 if dtype == torch.bfloat16 else _lib.DTYPE_FP16,
+                                          torch.cuda.current_stream().cuda_stream)
+    _lib.check(code, "probe")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(d, ref, rtol=1e-4, atol=1e-3)
