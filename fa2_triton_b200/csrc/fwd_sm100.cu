@@ -123,9 +123,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   // setmaxnreg at the top of each role branch (ptxas widens the budget only for dominated code):
-  // 2 softmax warpgroups x 128 x 208 + 1 issue warpgroup x 128 x 96 = 65536 registers
+  // pool = 384 threads x 168 launch registers = 64512 = 2 softmax warpgroups x 128 x 208 + 1 issue warpgroup x 128 x 88
   if (warp >= 8) {
-    reg_dealloc<96>();
+    reg_dealloc<88>();
   if (warp == 9) {
     // ======================================= TMA producer =======================================
     if (lane == 0 && nblk_max > 0) {
