@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the FlashAttention-2 hot path on B200 (contract: see README / DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4|cfg5]
+
+One "step" = one pass of the hot path over one batch of synthetic tensors (seed 0, Q/K/V ~ N(0, 0.5^2),
+dO ~ N(0, 1): the recipe of the reference's tests/utils.py:21-25). Default workload = BASELINE.json configs[2]
+(the configuration its metric is quoted on): bf16 fwd+bwd, B=4 H=32 S=4096 D=128, causal, deterministic dQ, PER GPU
+(weak scaling: the global batch is 4*N, sharded by batch with no collective on the data path).
+
+Rank 0 prints ONE JSON line: metric/value (device-timed, inputs resident in HBM), e2e (host buffers in, host
+buffers out, through fa2_triton_b200.host_api), roofline of the dominant kernel, cpu_baseline, clocks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (B per GPU or global (see "shard"), H, S, D, causal, backward, shard mode)
+    "cfg2": dict(B=4, H=32, S=4096, D=128, causal=True, bwd=False, scaling="weak"),
+    "cfg3": dict(B=4, H=32, S=4096, D=128, causal=True, bwd=True, scaling="weak"),
+    "cfg4": dict(B=2, H=16, S=16384, D=64, causal=False, bwd=True, scaling="weak"),
+    "cfg5": dict(B=32, H=32, S=8192, D=128, causal=True, bwd=True, scaling="strong"),
+}
+METRIC = "fwd+bwd TFLOP/s (bf16, causal, S=4096, D=128)"
+
+
+def fa_flops(B, H, Sq, Sk, D, causal, bwd):
+    """Algorithmic FLOPs: fwd = 4 B H Sq Sk D (x 1/2 causal), bwd = 2.5 x fwd."""
+    f = 4.0 * B * H * Sq * Sk * D * (0.5 if causal else 1.0)
+    return f * (3.5 if bwd else 1.0)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(burst=float(d["bf16_tflops"]), sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    hbm=float(d["hbm_gbs"]), source="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: clocks are reported as unknown, never invented
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_inputs(B, H, S, D, device, seed, torch):
+    """Q, K, V ~ N(0, 0.5^2), dO ~ N(0, 1) in bf16, generated on the device from a seeded generator."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    shape = (B, S, H, D)
+    out = []
+    for std in (0.5, 0.5, 0.5, 1.0):
+        t = torch.empty(shape, dtype=torch.bfloat16, device=device)
+        for b in range(B):  # per batch element: keeps the fp32 staging small
+            t[b] = torch.empty(shape[1:], dtype=torch.float32, device=device).normal_(0, std, generator=g).to(torch.bfloat16)
+        out.append(t)
+    return out
+
+
+def cpu_baseline_run(torch, w, steps, warmup, budget_s=20.0):
+    """Times the eager-PyTorch port of the reference's CPU path (oracle/eager_reference.py) on a bounded (b, h)
+    sample of the workload; the oracle's cost is exactly linear in B*H so the rate carries over."""
+    from oracle import eager_reference as er
+
+    threads = torch.get_num_threads()
+    S, D, causal, bwd = w["S"], w["D"], w["causal"], w["bwd"]
+    S_s = min(S, 4096)  # keep the S x S fp32 score tensors within a few hundred MB
+
+    def one(hs):
+        g = torch.Generator().manual_seed(0)
+        q, k, v = (torch.empty(1, S_s, hs, D).normal_(0, 0.5, generator=g).to(torch.bfloat16) for _ in range(3))
+        do = torch.empty(1, S_s, hs, D).normal_(0, 1.0, generator=g).to(torch.bfloat16)
+        t0 = time.perf_counter()
+        if bwd:
+            er.fwd_bwd(q, k, v, do, causal=causal)
+        else:
+            er.flash_attn_reference(q, k, v, causal=causal)
+        return time.perf_counter() - t0
+
+    one(1)
+    t1 = one(1)
+    total = max(1, steps + warmup)
+    hs = int(max(1, min(8, budget_s / total / max(t1, 1e-3))))
+    for _ in range(warmup):
+        one(hs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one(hs)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    flops = fa_flops(1, hs, S_s, S_s, D, causal, bwd)
+    return dict(value=flops / dt / 1e12, unit="TFLOP/s", cores=threads, kind="port",
+                sample=f"B=1,H={hs},S={S_s},D={D},causal={causal},{'fwd+bwd' if bwd else 'fwd'}; "
+                       f"{steps} steps of {dt * 1e3:.0f} ms; eager PyTorch fp32 math on bf16 inputs; "
+                       f"os.cpu_count()={os.cpu_count()}"), dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    w = WORKLOADS[args.workload]
+    cb, dt = cpu_baseline_run(torch, w, args.steps, args.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, w), "timed_sample": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(key, w):
+    return (f"{key}: bf16 {'fwd+bwd' if w['bwd'] else 'fwd'} B={w['B']},H={w['H']},S={w['S']},D={w['D']} "
+            f"{'causal' if w['causal'] else 'non-causal'}" + (", deterministic dQ" if w["bwd"] else ""))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--atomic", action="store_true", help="dQ in arrival order (fast mode) instead of deterministic")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import fa2_triton_b200 as fa2
+    from fa2_triton_b200 import _lib, shard
+    from fa2_triton_b200.host_api import HostAttention
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device - this path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    fa2.set_deterministic(not args.atomic)
+
+    w = dict(WORKLOADS[args.workload])
+    H, S, D, causal, bwd = w["H"], w["S"], w["D"], w["causal"], w["bwd"]
+    if w["scaling"] == "weak":
+        B_local, B_global = w["B"], w["B"] * world
+        seed = 0 + rank  # every rank owns different batch elements of the global batch
+    else:  # strong: the global (b, h) units are partitioned; this rank materialises only its own slices
+        B_global = w["B"]
+        blocks = shard.merge_spans(shard.partition(B_global, H, world, rank), H)
+        assert len(blocks) == 1 and blocks[0][2] == 0 and blocks[0][3] == H, "cfg5 shards by whole batch elements"
+        B_local = blocks[0][1] - blocks[0][0]
+        seed = 0 + rank
+
+    q, k, v, do = make_inputs(B_local, H, S, D, dev, seed, torch)
+    flops_local = fa_flops(B_local, H, S, S, D, causal, bwd)
+    flops_global = fa_flops(B_global, H, S, S, D, causal, bwd)
+
+    def step():
+        if bwd:
+            qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
+            out = fa2.flash_attn_func(qq, kk, vv, causal=causal)
+            return torch.autograd.grad(out, (qq, kk, vv), do)
+        return fa2.flash_attn_func(q, k, v, causal=causal)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---------------------------------------------- timed region ------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = flops_global / (ms_step * 1e-3) / 1e12
+
+    # -------------------------------- per-kernel timing (roofline of the dominant kernel) ------------------------
+    pk = peaks()
+    kern = {}
+    n_rep = min(args.steps, 20)
+    o, lse, scale, _ = fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
+    stream = torch.cuda.current_stream().cuda_stream
+    S_pad = math.ceil(S / 128) * 128
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    acc = {"fwd": 0.0, "delta": 0.0, "bwd": 0.0, "dq_convert": 0.0}
+    if bwd:
+        delta = torch.empty_like(lse)
+        dq = torch.empty_like(q)
+        dk, dv = torch.empty_like(k), torch.empty_like(v)
+        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, 1)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    for _ in range(n_rep):
+        marks = [ev() for _ in range(5)]
+        marks[0].record()
+        fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
+        marks[1].record()
+        if bwd:
+            _lib.check(lib.fa2_sm100_bwd_delta(o.data_ptr(), do.data_ptr(), delta.data_ptr(), B_local, H, S, D,
+                                               _lib.strides3(o), _lib.strides3(do), S_pad, 17, ws.data_ptr(), ws_bytes,
+                                               stream), "delta")
+            marks[2].record()
+            _lib.check(lib.fa2_sm100_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(),
+                                         delta.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), ws_bytes,
+                                         B_local, H, H, S, S, D, _lib.strides3(do), _lib.strides3(q), _lib.strides3(k),
+                                         _lib.strides3(v), _lib.strides3(dk), _lib.strides3(dv), S_pad, scale,
+                                         int(causal), int(not args.atomic), 17, stream), "bwd")
+            marks[3].record()
+            _lib.check(lib.fa2_sm100_dq_convert(ws.data_ptr(), dq.data_ptr(), B_local, H, S, D, _lib.strides3(dq),
+                                                scale, 17, stream), "dq_convert")
+            marks[4].record()
+        torch.cuda.synchronize()
+        acc["fwd"] += marks[0].elapsed_time(marks[1])
+        if bwd:
+            acc["delta"] += marks[1].elapsed_time(marks[2])
+            acc["bwd"] += marks[2].elapsed_time(marks[3])
+            acc["dq_convert"] += marks[3].elapsed_time(marks[4])
+    kern = {k_: v_ / n_rep for k_, v_ in acc.items() if v_ > 0}
+    f_fwd = fa_flops(B_local, H, S, S, D, causal, False)
+    if bwd:
+        dom, dom_flops = "fa2_bwd_kernel", 2.5 * f_fwd
+        dom_ms = kern["bwd"]
+    else:
+        dom, dom_flops = "fa2_fwd_kernel", f_fwd
+        dom_ms = kern["fwd"]
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["burst"], "unit": "TFLOP/s",
+                "frac": achieved / pk["burst"], "traffic": traffic, "peak_source": pk["source"] + " burst (kernel timed alone)",
+                "frac_of_sustained": achieved / pk["sustained"], "frac_of_nominal_2250": achieved / 2250.0,
+                "fwd_kernel_tflops": f_fwd / (kern["fwd"] * 1e-3) / 1e12, "kernel_ms": kern}
+
+    # ------------------------------------------------- e2e --------------------------------------------------------
+    e2e = None
+    if bwd and not args.no_e2e:
+        plan = HostAttention(q.shape, k.shape, torch.bfloat16, dev)
+        hp = [t.cpu().pin_memory() for t in (q, k, v, do)]
+        for _ in range(2):
+            plan(*hp, causal=causal)
+        n_e2e = max(3, min(args.steps, 10))
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            res = plan(*hp, causal=causal)
+            _ = float(res[0][0, 0, 0, 0])  # the host really holds the result
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": flops_global / tt.item() / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": plan.h2d_bytes,
+               "d2h_bytes_per_step": plan.d2h_bytes, "ms_per_step": tt.item() * 1e3, "steps": n_e2e,
+               "api": "fa2_triton_b200.host_api.HostAttention (pinned host q,k,v,dO in; o,dq,dk,dv out; "
+                      f"{plan.chunks} batch chunks over 3 streams)"}
+
+    # -------------------------------------------- CPU baseline (rank 0, N=1) --------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_baseline_run(torch, w, steps=3, warmup=1, budget_s=20.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": w["scaling"],
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, w), "per_gpu_batch": B_local, "global_batch": B_global,
+                       "sharding": f"batch x head units over {world} GPU(s), no data-path collective",
+                       "dq_mode": "atomic" if args.atomic else "deterministic",
+                       "l2": "inputs (q,k,v,o,dO = 5 x 128 MiB at cfg3) exceed the 126 MB L2; no explicit flush",
+                       "api": "fa2_triton_b200.flash_attn_func + torch.autograd.grad"},
+            "frac_of_measured_burst_peak": value / world / pk["burst"],
+            "frac_of_measured_sustained_peak": value / world / pk["sustained"],
+            "frac_of_nominal_peak_2250": value / world / 2250.0,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": args.steps * (4 if bwd else 1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,7 @@ SIGNATURES = {
     "fa2_sm100_fwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 4
                       + [_c_int64, _c_float, _c_int, _c_int, _c_void_p]),
     "fa2_sm100_bwd_delta": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)] * 2
-                            + [_c_int64, _c_int, _c_void_p]),
+                            + [_c_int64, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "fa2_sm100_bwd_workspace_bytes": (_c_size_t, [_c_int] * 6),
     "fa2_sm100_bwd": (_c_int, [_c_void_p] * 9 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 6
                       + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_void_p]),

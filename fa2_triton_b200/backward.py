@@ -40,10 +40,14 @@ def _flash_attn_backward(
     softmax_scale: Optional[float],
     dropout_seed: Optional[int],
     deterministic: Optional[bool] = None,
+    dq_dtype: Optional[torch.dtype] = None,
 ) -> Tuple[Tensor, Tensor, Tensor]:
     """Returns ``(dq, dk, dv)`` like src/backward/caller.py:178: ``dq`` is fp32 ``[B, Sq, Hq, D]``
     (src/backward/caller.py:86), ``dk``/``dv`` are ``[B, Sk, Hkv, D]`` in the input dtype with the GQA
-    head-group sum (src/backward/caller.py:163-165) already applied inside the kernel."""
+    head-group sum (src/backward/caller.py:163-165) already applied inside the kernel.
+
+    ``dq_dtype`` (extension): write dq in that dtype instead of fp32. The autograd wrapper passes the input
+    dtype - the rounding autograd would apply to the reference's fp32 dq anyway - and saves one pass over dq."""
     _reject_out_of_scope(attention_mask, bias, dropout_p)
     dO = dO.contiguous() if dO.stride(-1) != 1 else dO
     batch_size, seqlen_q, nheads_q, head_dim = q.shape
@@ -65,7 +69,7 @@ def _flash_attn_backward(
     with torch.cuda.device(q.device):
         stream = _stream_ptr(q.device)
         delta = torch.empty_like(lse)
-        dq = torch.empty_like(q, dtype=torch.float32)
+        dq = torch.empty_like(q, dtype=torch.float32 if dq_dtype is None else dq_dtype)
         dk = torch.empty_like(k)
         dv = torch.empty_like(v)
         ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, int(det))
@@ -73,7 +77,7 @@ def _flash_attn_backward(
 
         code = lib.fa2_sm100_bwd_delta(
             o.data_ptr(), dO.data_ptr(), delta.data_ptr(), batch_size, nheads_q, seqlen_q, head_dim,
-            _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt, stream)
+            _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt, workspace.data_ptr(), ws_bytes, stream)
         _lib.check(code, "fa2_sm100_bwd_delta")
         code = lib.fa2_sm100_bwd(
             dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(), delta.data_ptr(),
@@ -85,6 +89,6 @@ def _flash_attn_backward(
         _lib.check(code, "fa2_sm100_bwd")
         code = lib.fa2_sm100_dq_convert(
             workspace.data_ptr(), dq.data_ptr(), batch_size, nheads_q, seqlen_q, head_dim,
-            _lib.strides3(dq), softmax_scale, _lib.DTYPE_FP32, stream)
+            _lib.strides3(dq), softmax_scale, encode_dtype(dq), stream)
         _lib.check(code, "fa2_sm100_dq_convert")
     return dq, dk, dv

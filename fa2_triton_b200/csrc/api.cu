@@ -122,7 +122,7 @@ int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* l
 
 int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, int Hq, int Sq, int D,
                         const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride, int dtype,
-                        void* stream) {
+                        void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_common(B, Hq, Hq, Sq, 1, D, dtype)) return e;
   if (!o || !dout || !delta) return fail(FA2_E_NULL_POINTER, "o / dout / delta: null pointer");
   if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
@@ -135,6 +135,15 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, in
   p.B = B; p.Hq = Hq; p.Sq = Sq; p.D = D;
   p.lse_stride = static_cast<int>(lse_row_stride);
   for (int i = 0; i < 3; ++i) { p.o_strides[i] = o_strides[i]; p.do_strides[i] = do_strides[i]; }
+  if (workspace) {
+    const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, 1, D, 1);
+    if (workspace_bytes < need)
+      return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FA2_E_BAD_ALIGNMENT, "workspace not 16-byte aligned");
+    p.dq_accum = static_cast<float*>(workspace);
+    p.dq_sem = reinterpret_cast<int*>(static_cast<char*>(workspace) +
+                                      static_cast<size_t>(B) * Hq * lse_row_stride * D * sizeof(float));
+  }
   cudaError_t ce = fa2::launch_delta(dtype == FA2_DTYPE_BF16, p, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd_delta launch");
   return 0;
@@ -172,8 +181,7 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   if (int e = make_tmap_bshd(&tdv, dv, dtype, B, Sk, Hkv, D, dv_strides, 128, "dv")) return e;
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t ce = cudaMemsetAsync(workspace, 0, need, st);
-  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd workspace memset");
+  cudaError_t ce = cudaSuccess;
 
   const int sq_pad = round_up(Sq, 128);
   fa2::BwdParams p{};

@@ -126,6 +126,19 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
   for (int off = kThreadsPerRow / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
   if (part == 0 && row < p.lse_stride)
     p.delta[(static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + row] = acc;  // padded rows: 0
+  // Clear this CTA's share of the backward workspace (fp32 dQ accumulator + ordered-reduction tickets), so the
+  // fused kernel that follows on the stream needs no separate memset: kRowsPerBlock * D floats = 2 float4 / thread.
+  if (p.dq_accum != nullptr) {
+    const int64_t bh = static_cast<int64_t>(batch) * p.Hq + head;
+    float4* dst = reinterpret_cast<float4*>(p.dq_accum + (bh * p.lse_stride + static_cast<int64_t>(blockIdx.x) * kRowsPerBlock) * D);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    dst[threadIdx.x] = z;
+    dst[threadIdx.x + 256] = z;
+    if (blockIdx.x == 0 && p.dq_sem != nullptr) {
+      const int tiles = p.lse_stride / 128;
+      for (int i = threadIdx.x; i < tiles; i += 256) p.dq_sem[bh * tiles + i] = 0;
+    }
+  }
 }
 
 cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream) {

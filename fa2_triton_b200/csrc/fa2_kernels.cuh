@@ -33,6 +33,8 @@ struct DeltaParams {
   int lse_stride;
   int64_t o_strides[3];   // batch, head, seq (elements)
   int64_t do_strides[3];
+  float* dq_accum;  // optional: backward workspace to clear ([B, Hq, lse_stride, D] fp32), or nullptr
+  int* dq_sem;      // optional: [B, Hq, lse_stride / 128] tickets to clear, or nullptr
 };
 cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream);
 

@@ -308,6 +308,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (nblk > 0) {
         mbar_wait(&o_full[t], 0);
         tcgen05_fence_after();
+      } else if (nblk_max > 0) {
+        // fully masked tile next to a live one: its Q tile is still being loaded under the shared q_full
+        // barrier; the zero rows staged below must not be overwritten by that load
+        mbar_wait(q_full, 0);
       }
       uint8_t* sO = sQ + t * L::kTileBytes;  // the Q tile is dead once o_full fired
 #pragma unroll

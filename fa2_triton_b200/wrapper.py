@@ -65,6 +65,7 @@ class FlashAttnFunc(torch.autograd.Function):
             causal=ctx.causal,
             softmax_scale=ctx.softmax_scale,
             dropout_seed=ctx.dropout_seed,
+            dq_dtype=q.dtype,
         )
         return dq, dk, dv, None, None, None, None, None, None
 

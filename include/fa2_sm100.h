@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 1
+#define FA2_SM100_ABI_VERSION 2
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -63,18 +63,20 @@ int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   const int64_t o_strides[3], int64_t lse_row_stride,
                   float softmax_scale, int causal, int dtype, void* stream);
 
-/* delta[b, h, i] = sum_d O[b, i, h, d] * dO[b, i, h, d] in fp32; rows in [Sq, lse_row_stride) are set to 0. */
+/* delta[b, h, i] = sum_d O[b, i, h, d] * dO[b, i, h, d] in fp32; rows in [Sq, lse_row_stride) are set to 0.
+ * If `workspace` is not NULL the same launch also zero-fills it (the reference zero-allocates dq at
+ * src/backward/caller.py:86); that is the state fa2_sm100_bwd expects to find its workspace in. */
 int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
                         int B, int Hq, int Sq, int D,
                         const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride,
-                        int dtype, void* stream);
+                        int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Bytes of scratch fa2_sm100_bwd needs: the fp32 dQ accumulator plus (deterministic mode) one int per
  * (batch, head, 128-row query tile). The workspace must be 16-byte aligned. */
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic);
 
 /* dK, dV (input dtype, [B, Sk, Hkv, D]) and the fp32 dQ accumulator inside `workspace`.
- * The call zero-fills what it needs of the workspace itself (cudaMemsetAsync on `stream`).
+ * The workspace must be all zero on entry: pass it to fa2_sm100_bwd_delta (same stream) or clear it yourself.
  * deterministic != 0: contributions to each dQ tile are added in a fixed key-block order, results are
  * bit-identical run to run; deterministic == 0: same adds in arrival order (fast mode). */
 int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,

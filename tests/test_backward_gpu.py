@@ -116,7 +116,8 @@ def test_delta_kernel():
     do = torch.randn(B, S, H, D, device=DEV, dtype=torch.bfloat16)
     delta = torch.full((B, H, 384), float("nan"), device=DEV)
     code = lib.fa2_sm100_bwd_delta(o.data_ptr(), do.data_ptr(), delta.data_ptr(), B, H, S, D, _lib.strides3(o),
-                                   _lib.strides3(do), 384, _lib.DTYPE_BF16, torch.cuda.current_stream().cuda_stream)
+                                   _lib.strides3(do), 384, _lib.DTYPE_BF16, None, 0,
+                                   torch.cuda.current_stream().cuda_stream)
     _lib.check(code, "delta")
     ref = (o.float() * do.float()).sum(-1).permute(0, 2, 1)
     torch.testing.assert_close(delta[:, :, :S], ref, rtol=1e-4, atol=1e-3)
