@@ -273,42 +273,45 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     S_pad = math.ceil(S / 128) * 128
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    acc = {"fwd": 0.0, "delta": 0.0, "bwd": 0.0, "dq_convert": 0.0}
+    acc = {"fwd": 0.0, "delta": 0.0, "bwd": 0.0}
     if bwd:
         delta = torch.empty_like(lse)
         dq = torch.empty_like(q)
         dk, dv = torch.empty_like(k), torch.empty_like(v)
-        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, 1)
-        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dq_mode = 0 if args.atomic else 1
+        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, dq_mode)
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        ws_ptr = ws.data_ptr() if ws_bytes else None
+    o2, lse2 = torch.empty_like(o), torch.empty_like(lse)
     for _ in range(n_rep):
         marks = [ev() for _ in range(5)]
         marks[0].record()
-        fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
+        _lib.check(lib.fa2_sm100_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o2.data_ptr(), lse2.data_ptr(),
+                                     B_local, H, H, S, S, D, _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
+                                     _lib.strides3(o2), S_pad, scale, int(causal), 17, stream), "fwd")
         marks[1].record()
         if bwd:
             _lib.check(lib.fa2_sm100_bwd_delta(o.data_ptr(), do.data_ptr(), delta.data_ptr(), B_local, H, S, D,
-                                               _lib.strides3(o), _lib.strides3(do), S_pad, 17, ws.data_ptr(), ws_bytes,
+                                               _lib.strides3(o), _lib.strides3(do), S_pad, 17, ws_ptr, ws_bytes,
                                                stream), "delta")
             marks[2].record()
             _lib.check(lib.fa2_sm100_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(),
-                                         delta.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), ws_bytes,
+                                         delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws_ptr, ws_bytes,
                                          B_local, H, H, S, S, D, _lib.strides3(do), _lib.strides3(q), _lib.strides3(k),
-                                         _lib.strides3(v), _lib.strides3(dk), _lib.strides3(dv), S_pad, scale,
-                                         int(causal), int(not args.atomic), 17, stream), "bwd")
+                                         _lib.strides3(v), _lib.strides3(dq), _lib.strides3(dk), _lib.strides3(dv),
+                                         S_pad, scale, int(causal), dq_mode, 17, 17, stream), "bwd")
             marks[3].record()
-            _lib.check(lib.fa2_sm100_dq_convert(ws.data_ptr(), dq.data_ptr(), B_local, H, S, D, _lib.strides3(dq),
-                                                scale, 17, stream), "dq_convert")
             marks[4].record()
         torch.cuda.synchronize()
         acc["fwd"] += marks[0].elapsed_time(marks[1])
         if bwd:
             acc["delta"] += marks[1].elapsed_time(marks[2])
             acc["bwd"] += marks[2].elapsed_time(marks[3])
-            acc["dq_convert"] += marks[3].elapsed_time(marks[4])
     kern = {k_: v_ / n_rep for k_, v_ in acc.items() if v_ > 0}
     f_fwd = fa_flops(B_local, H, S, S, D, causal, False)
     if bwd:
-        dom, dom_flops = "fa2_bwd_kernel", 2.5 * f_fwd
+        dom = "fa2_bwd_kernel + fa2_dq_convert_kernel" if args.atomic else "fa2_bwd_kernel (dK/dV) + fa2_bwd_dq_kernel"
+        dom_flops = 2.5 * f_fwd
         dom_ms = kern["bwd"]
     else:
         dom, dom_flops = "fa2_fwd_kernel", f_fwd
@@ -369,7 +372,7 @@ def main():
             "frac_of_measured_sustained_peak": value / world / pk["sustained"],
             "frac_of_nominal_peak_2250": value / world / 2250.0,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * (4 if bwd else 1),
+            "gpu_launches": args.steps * (4 if bwd else 1),  # fwd, delta, dK/dV (+dQ partials), dQ kernel or dQ convert
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -24,6 +24,8 @@ E_NULL_POINTER = -5
 E_WORKSPACE_TOO_SMALL = -6
 E_NO_DRIVER = -7
 
+DQ_ATOMIC, DQ_DETERMINISTIC, DQ_FUSED_ORDERED = 0, 1, 2  # the `deterministic` argument of fa2_sm100_bwd
+
 DTYPE_FP16 = 16
 DTYPE_BF16 = 17
 DTYPE_FP32 = 32
@@ -41,8 +43,8 @@ SIGNATURES = {
     "fa2_sm100_bwd_delta": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)] * 2
                             + [_c_int64, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "fa2_sm100_bwd_workspace_bytes": (_c_size_t, [_c_int] * 6),
-    "fa2_sm100_bwd": (_c_int, [_c_void_p] * 9 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 6
-                      + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_void_p]),
+    "fa2_sm100_bwd": (_c_int, [_c_void_p] * 10 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 7
+                      + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "fa2_sm100_dq_convert": (_c_int, [_c_void_p] * 2 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)]
                              + [_c_float, _c_int, _c_void_p]),
     "fa2_sm100_debug_umma_probe": (_c_int, [_c_void_p] * 3 + [_c_int] * 5 + [_c_void_p]),

@@ -11,15 +11,18 @@ from torch import Tensor
 from . import _lib
 from .forward import _reject_out_of_scope, _stream_ptr, encode_dtype
 
-# Process-wide default for how dQ contributions are summed. True: fixed key-block order, bit-identical
-# run to run (what the reference's atomics-free kernel guarantees, src/backward/kernel.py:154-182).
-# False: arrival order ("atomic fast mode").
+# Process-wide default for how dQ contributions are summed.
+#   True / 1 : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
+#              fixed order, no atomics (what the reference's kernel does, src/backward/kernel.py:154-182).
+#   False / 0: atomic fast mode - the dK/dV kernel also forms dQ partial products and adds them into an fp32
+#              accumulator in arrival order (5 instead of 7 matrix products per block pair).
+#   2        : the fused kernel with the adds serialised per query tile by a ticket (bit-repeatable as well).
 _DETERMINISTIC = True
 
 
-def set_deterministic(flag: bool) -> None:
+def set_deterministic(flag) -> None:
     global _DETERMINISTIC
-    _DETERMINISTIC = bool(flag)
+    _DETERMINISTIC = flag if flag in (0, 1, 2) and not isinstance(flag, bool) else bool(flag)
 
 
 def is_deterministic() -> bool:
@@ -62,7 +65,8 @@ def _flash_attn_backward(
     assert q.is_cuda and k.is_cuda and v.is_cuda and o.is_cuda and dO.is_cuda and lse.is_cuda
     assert q.dtype == k.dtype == v.dtype == o.dtype == dO.dtype, "All tensors must have the same type"
     assert lse.dtype == torch.float32 and lse.is_contiguous()
-    det = _DETERMINISTIC if deterministic is None else bool(deterministic)
+    det = _DETERMINISTIC if deterministic is None else deterministic
+    mode = int(det) if det in (0, 1, 2) else int(bool(det))  # True/False, or one of _lib.DQ_*
 
     lib = _lib.load()
     dt = encode_dtype(q)
@@ -72,23 +76,21 @@ def _flash_attn_backward(
         dq = torch.empty_like(q, dtype=torch.float32 if dq_dtype is None else dq_dtype)
         dk = torch.empty_like(k)
         dv = torch.empty_like(v)
-        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, int(det))
-        workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, mode)
+        workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
+        ws_ptr = workspace.data_ptr() if ws_bytes else None
 
+        # delta = rowsum(O * dO); the same launch clears the dQ accumulator when there is one
         code = lib.fa2_sm100_bwd_delta(
             o.data_ptr(), dO.data_ptr(), delta.data_ptr(), batch_size, nheads_q, seqlen_q, head_dim,
-            _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt, workspace.data_ptr(), ws_bytes, stream)
+            _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt, ws_ptr, ws_bytes, stream)
         _lib.check(code, "fa2_sm100_bwd_delta")
         code = lib.fa2_sm100_bwd(
             dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-            dk.data_ptr(), dv.data_ptr(), workspace.data_ptr(), ws_bytes,
+            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws_ptr, ws_bytes,
             batch_size, nheads_q, nheads_kv, seqlen_q, seqlen_k, head_dim,
             _lib.strides3(dO), _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
-            _lib.strides3(dk), _lib.strides3(dv),
-            max_seqlen_q_rounded, softmax_scale, int(bool(causal)), int(det), dt, stream)
+            _lib.strides3(dq), _lib.strides3(dk), _lib.strides3(dv),
+            max_seqlen_q_rounded, softmax_scale, int(bool(causal)), mode, dt, encode_dtype(dq), stream)
         _lib.check(code, "fa2_sm100_bwd")
-        code = lib.fa2_sm100_dq_convert(
-            workspace.data_ptr(), dq.data_ptr(), batch_size, nheads_q, seqlen_q, head_dim,
-            _lib.strides3(dq), softmax_scale, encode_dtype(dq), stream)
-        _lib.check(code, "fa2_sm100_dq_convert")
     return dq, dk, dv

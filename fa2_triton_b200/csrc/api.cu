@@ -136,7 +136,7 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, in
   p.lse_stride = static_cast<int>(lse_row_stride);
   for (int i = 0; i < 3; ++i) { p.o_strides[i] = o_strides[i]; p.do_strides[i] = do_strides[i]; }
   if (workspace) {
-    const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, 1, D, 1);
+    const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, 1, D, FA2_DQ_ATOMIC);
     if (workspace_bytes < need)
       return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
     if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FA2_E_BAD_ALIGNMENT, "workspace not 16-byte aligned");
@@ -149,10 +149,13 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, in
   return 0;
 }
 
+int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq, int D, const int64_t dq_strides[3],
+                         float softmax_scale, int out_dtype, void* stream);
+
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic) {
   (void)Sk;
-  (void)deterministic;
   if (B < 1 || Hq < 1 || Sq < 1 || D < 1) return 0;
+  if (deterministic == FA2_DQ_DETERMINISTIC) return 0;  // dQ is produced by its own kernel, no accumulator
   const size_t sq_pad = static_cast<size_t>(round_up(Sq, 128));
   const size_t accum = static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float);
   const size_t sem = static_cast<size_t>(B) * Hq * (sq_pad / 128) * sizeof(int);
@@ -160,18 +163,28 @@ size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int d
 }
 
 int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v, const float* lse, const float* delta,
-                  void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int Hq, int Hkv, int Sq, int Sk,
-                  int D, const int64_t do_strides[3], const int64_t q_strides[3], const int64_t k_strides[3],
-                  const int64_t v_strides[3], const int64_t dk_strides[3], const int64_t dv_strides[3],
-                  int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype, void* stream) {
+                  void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int Hq, int Hkv,
+                  int Sq, int Sk, int D, const int64_t do_strides[3], const int64_t q_strides[3],
+                  const int64_t k_strides[3], const int64_t v_strides[3], const int64_t dq_strides[3],
+                  const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride, float softmax_scale,
+                  int causal, int deterministic, int dtype, int dq_dtype, void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
-  if (!lse || !delta || !workspace) return fail(FA2_E_NULL_POINTER, "lse / delta / workspace: null pointer");
+  if (!lse || !delta || !dq) return fail(FA2_E_NULL_POINTER, "lse / delta / dq: null pointer");
   if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
   if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
+  if (deterministic < 0 || deterministic > 2) return fail(FA2_E_BAD_SHAPE, "deterministic must be 0, 1 or 2");
+  if (dq_dtype != dtype && dq_dtype != FA2_DTYPE_FP32)
+    return fail(FA2_E_UNSUPPORTED_DTYPE, "dq_dtype %d: must be the input dtype (%d) or 32 (fp32)", dq_dtype, dtype);
+  if (reinterpret_cast<uintptr_t>(dq) % 16) return fail(FA2_E_BAD_ALIGNMENT, "dq: base not 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    if (dq_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "dq: strides must be multiples of 8 elements");
   const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, Sk, D, deterministic);
-  if (workspace_bytes < need)
-    return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
-  if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FA2_E_BAD_ALIGNMENT, "workspace not 16-byte aligned");
+  if (need > 0) {
+    if (!workspace) return fail(FA2_E_NULL_POINTER, "workspace: null pointer");
+    if (workspace_bytes < need)
+      return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FA2_E_BAD_ALIGNMENT, "workspace not 16-byte aligned");
+  }
   CUtensorMap tq, tk, tv, tdo, tdk, tdv;
   if (int e = make_tmap_bshd(&tq, q, dtype, B, Sq, Hq, D, q_strides, 128, "q")) return e;
   if (int e = make_tmap_bshd(&tk, k, dtype, B, Sk, Hkv, D, k_strides, 128, "k")) return e;
@@ -181,22 +194,41 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   if (int e = make_tmap_bshd(&tdv, dv, dtype, B, Sk, Hkv, D, dv_strides, 128, "dv")) return e;
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t ce = cudaSuccess;
-
   const int sq_pad = round_up(Sq, 128);
+  const bool fused = deterministic != FA2_DQ_DETERMINISTIC;
   fa2::BwdParams p{};
   p.lse = lse; p.delta = delta;
   p.dq_accum = static_cast<float*>(workspace);
-  p.dq_sem = reinterpret_cast<int*>(static_cast<char*>(workspace) + static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float));
+  p.dq_sem = fused ? reinterpret_cast<int*>(static_cast<char*>(workspace) + static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float))
+                   : nullptr;
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk;
   p.lse_stride = static_cast<int>(lse_row_stride);
   p.sq_pad = sq_pad;
   p.softmax_scale = softmax_scale;
   p.scale_log2 = softmax_scale * kLog2e;
   p.causal = causal ? 1 : 0;
-  p.deterministic = deterministic ? 1 : 0;
-  ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, tdk, tdv, p, st);
+  p.deterministic = deterministic == FA2_DQ_FUSED_ORDERED ? 1 : 0;
+  cudaError_t ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
+
+  if (fused) {
+    // dQ accumulator -> caller's tensor
+    return fa2_sm100_dq_convert(workspace, dq, B, Hq, Sq, D, dq_strides, softmax_scale, dq_dtype, stream);
+  }
+  CUtensorMap tdq = tq;  // placeholder when dq is fp32 (the kernel then stores through plain pointers)
+  if (dq_dtype == dtype)
+    if (int e = make_tmap_bshd(&tdq, dq, dtype, B, Sq, Hq, D, dq_strides, 128, "dq")) return e;
+  fa2::DqParams d{};
+  d.lse = lse; d.delta = delta; d.dq = dq;
+  for (int i = 0; i < 3; ++i) d.dq_strides[i] = dq_strides[i];
+  d.dq_is_16bit = dq_dtype == dtype ? 1 : 0;
+  d.B = B; d.Hq = Hq; d.Hkv = Hkv; d.Sq = Sq; d.Sk = Sk;
+  d.lse_stride = static_cast<int>(lse_row_stride);
+  d.softmax_scale = softmax_scale;
+  d.scale_log2 = softmax_scale * kLog2e;
+  d.causal = causal ? 1 : 0;
+  ce = fa2::launch_bwd_dq(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, tdq, d, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ launch");
   return 0;
 }
 
@@ -222,6 +254,12 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_dq_convert launch");
   return 0;
 }
+
+#ifdef FA2_TRACE
+int fa2_sm100_debug_fetch_trace(int which, long long* host, size_t n) {
+  return static_cast<int>(which == 0 ? fa2::fetch_fwd_trace(host, n) : fa2::fetch_bwd_trace(host, n));
+}
+#endif
 
 int fa2_sm100_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_mode, int b_mode, int dtype,
                                void* stream) {

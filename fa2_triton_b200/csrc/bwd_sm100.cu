@@ -26,6 +26,21 @@
 
 namespace fa2 {
 
+#ifdef FA2_TRACE
+// Debug build only (make TRACE=1): clock64() stamps of one CTA's pipeline events, [role][iteration][event].
+__device__ long long g_bwd_trace[4 * 64 * 8];
+#define FA2_STAMP(role, it, ev)                                                                          \
+  do {                                                                                                   \
+    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 64)                  \
+      g_bwd_trace[((role) * 64 + (it)) * 8 + (ev)] = clock64();                                          \
+  } while (0)
+cudaError_t fetch_bwd_trace(long long* host, size_t n) {
+  return cudaMemcpyFromSymbol(host, g_bwd_trace, n * sizeof(long long));
+}
+#else
+#define FA2_STAMP(role, it, ev) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kBlk = 128;  // rows per Q block and per K/V block
@@ -36,20 +51,20 @@ constexpr int kRegsIssue = 56;
 
 template <int D>
 struct BwdSmem {
+  static constexpr int kQStages = 2;
   static constexpr int kTileBytes = kBlk * D * 2;     // K, V, Q, dO tiles
   static constexpr int kDsBytes = kBlk * kBlk * 2;    // dS^T tile: 2 sub-tiles [128 kv x 64 q]
-  static constexpr int kPanelBytes = kBlk * 64 * 4;   // one dQ panel: [128 q x 64 d] fp32
-  static constexpr bool kStagingAliasesDO = (D == 128);
+  static constexpr int kChunkBytes = kBlk * 32 * 4;   // dQ staging chunk: [128 q x 32 d] fp32 = 16 KB
   static constexpr int kKOff = 0;
   static constexpr int kVOff = kKOff + kTileBytes;
-  static constexpr int kQOff = kVOff + kTileBytes;          // 2 stages
-  static constexpr int kDOOff = kQOff + 2 * kTileBytes;     // 2 stages
-  static constexpr int kDsOff = kDOOff + 2 * kTileBytes;
-  static constexpr int kStageOff = kDsOff + kDsBytes;       // dQ staging (only when not aliased)
-  static constexpr int kLseOff = kStageOff + (kStagingAliasesDO ? 0 : kPanelBytes);  // 2 x 512 B
-  static constexpr int kDeltaOff = kLseOff + 2 * kBlk * 4;                            // 2 x 512 B
+  static constexpr int kQOff = kVOff + kTileBytes;                // kQStages stages
+  static constexpr int kDOOff = kQOff + kQStages * kTileBytes;    // 1 stage
+  static constexpr int kDsOff = kDOOff + kTileBytes;
+  static constexpr int kStageOff = kDsOff + kDsBytes;             // 2 chunks
+  static constexpr int kLseOff = kStageOff + 2 * kChunkBytes;     // kQStages x 512 B (rides with Q)
+  static constexpr int kDeltaOff = kLseOff + kQStages * kBlk * 4; // 2 x 512 B (rides with dO, own barriers)
   static constexpr int kBarOff = kDeltaOff + 2 * kBlk * 4;
-  static constexpr int kNumBars = 16;
+  static constexpr int kNumBars = 22;
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
   static constexpr int kBytes = kTmemSlotOff + 16;
   static_assert(kBytes <= 232448, "backward smem budget exceeded");
@@ -57,10 +72,11 @@ struct BwdSmem {
 
 enum BwdBar {
   kKvFull = 0,
-  kQFull = 1,    // [2]
-  kQEmpty = 3,   // [2]
-  kDoFull = 5,   // [2]
-  kDoEmpty = 7,  // [2]
+  kQFull = 1,   // [2]
+  kQEmpty = 3,  // [2]
+  kStageFull = 5,   // [2] dQ staging chunk written by the drain warps
+  kDoFull = 7,
+  kDoEmpty = 8,
   kSFull = 9,
   kPFull = 10,
   kDpFull = 11,
@@ -68,6 +84,8 @@ enum BwdBar {
   kDqFull = 13,
   kDqEmpty = 14,
   kDkvFull = 15,
+  kDeltaFull = 16,   // [2]
+  kStageEmpty = 18,  // [2] the bulk reduction has finished reading the chunk
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -77,6 +95,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -160,9 +179,20 @@ cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream) {
 // fused dK / dV / dQ
 // =================================================================================================
 // dQ accumulator layout (opaque workspace, undone by fa2_dq_convert_kernel):
-//   [B][Hq][Sq_pad/128 tiles][D/64 panels][128 rows][64 fp32], and inside a row the 16-byte chunk index is
-//   XOR-ed with (row & 7) so that the staging writes (thread = row) are bank-conflict free.
-template <int D, bool kBf16>
+//   [B][Hq][Sq_pad/128 tiles][D/32 chunks][128 rows][32 fp32], and inside a 128-byte row the 16-byte piece index
+//   is XOR-ed with (row & 7) so that the staging writes (thread = row) are bank-conflict free. One chunk is one
+//   16 KB cp.reduce.async.bulk (fp32 add performed by the L2 atomic units).
+// The reduction is asynchronous and paced by L2 (measured: ~22 B/clk/SM chip-wide, scripts/micro/red_bw.cu), so it
+// gets its own thread (warp 14) and a 2-chunk staging ring: the drain warps only ever wait for a free chunk, the
+// compute and MMA warps never wait for the reduction at all. (Adding from registers with REDG.128 instead keeps the
+// LSU busy for the whole L2 round trip and stalls the compute warps' shared-memory traffic behind it.)
+//
+// Tensor-pipe order per query block i (all five products are 128 x 128 x 128 at D = 128):
+//     dV(i) | S(i+1) | dQ(i) | dK(i) | dP(i+1)
+// dP(i+1) does not depend on P(i+1), so it is issued one block ahead: when the compute warps finish P(i+1) its dP
+// is already in tensor memory and dS follows immediately. dQ(i) goes before dK(i) so that the drain warps empty
+// the shared dP/dQ columns while dK(i) runs.
+template <int D, bool kBf16, bool kFusedDq>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -171,7 +201,7 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   using L = BwdSmem<D>;
   constexpr int kSub = D / 64;
   constexpr int kSubBytes = kBlk * 128;  // [128 rows x 64 x 16-bit]
-  constexpr int kPanels = D / 64;
+  constexpr int kQStages = L::kQStages;
   constexpr uint32_t kTmemS = 0, kTmemDV = 128, kTmemDK = 256, kTmemDP = 384;
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -223,12 +253,12 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp == 12) {
     if (lane == 0) {
       mbar_init(&bars[kKvFull], 1);
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < kQStages; ++s) {
         mbar_init(&bars[kQFull + s], 1);
         mbar_init(&bars[kQEmpty + s], 1);
-        mbar_init(&bars[kDoFull + s], 1);
-        mbar_init(&bars[kDoEmpty + s], 1);
       }
+      mbar_init(&bars[kDoFull], 1);
+      mbar_init(&bars[kDoEmpty], 1);
       mbar_init(&bars[kSFull], 1);
       mbar_init(&bars[kPFull], 256);
       mbar_init(&bars[kDpFull], 1);
@@ -236,6 +266,12 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&bars[kDqFull], 1);
       mbar_init(&bars[kDqEmpty], 128);
       mbar_init(&bars[kDkvFull], 1);
+      mbar_init(&bars[kDeltaFull + 0], 1);
+      mbar_init(&bars[kDeltaFull + 1], 1);
+      for (int c = 0; c < 2; ++c) {
+        mbar_init(&bars[kStageFull + c], 128);
+        mbar_init(&bars[kStageEmpty + c], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -244,7 +280,9 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // whole-TMEM allocation => base 0; the literal keeps tcgen05 addresses warp-uniform for ptxas (see fwd_sm100.cu)
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   // setmaxnreg sits at the top of each role's branch: ptxas only widens the register budget for code the
   // instruction dominates.
@@ -252,34 +290,38 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     reg_dealloc<kRegsIssue>();
   if (warp == 13) {
     // ========================================= TMA producer ========================================
-    if (lane == 0 && T > 0) {
+    if (T > 0 && elect_one()) {
       mbar_arrive_expect_tx(&bars[kKvFull], 2 * L::kTileBytes);
       for (int j = 0; j < kSub; ++j) {
         tma_load_4d(sK + j * kSubBytes, &tmap_k, &bars[kKvFull], j * 64, kv0, head_kv, batch);
         tma_load_4d(sV + j * kSubBytes, &tmap_v, &bars[kKvFull], j * 64, kv0, head_kv, batch);
       }
+      int qs = 0;
+      uint32_t qph = 0;
       for (int it = 0; it < T; ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
         const int head = head_kv * group + it / m_count;
         const int m = q_block_of(it);
-        const float* lse_src = p.lse + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
-        const float* delta_src = p.delta + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
-        mbar_wait(&bars[kQEmpty + st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars[kQFull + st], L::kTileBytes + kBlk * 4);
+        const int64_t row_off = (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
+        // Q(it) + its LSE and delta rows: ring of kQStages (released by dK(it - kQStages))
+        mbar_wait(&bars[kQEmpty + qs], qph ^ 1);
+        mbar_arrive_expect_tx(&bars[kQFull + qs], L::kTileBytes + kBlk * 4);
         for (int j = 0; j < kSub; ++j)
-          tma_load_4d(sQ + st * L::kTileBytes + j * kSubBytes, &tmap_q, &bars[kQFull + st], j * 64, m * kBlk, head, batch);
-        bulk_load_1d(sLse + st * kBlk, lse_src, kBlk * 4, &bars[kQFull + st]);
-        mbar_wait(&bars[kDoEmpty + st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars[kDoFull + st], L::kTileBytes + kBlk * 4);
+          tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, &tmap_q, &bars[kQFull + qs], j * 64, m * kBlk, head, batch);
+        bulk_load_1d(sLse + qs * kBlk, p.lse + row_off, kBlk * 4, &bars[kQFull + qs]);
+        // dO(it): single buffer, free again once dV(it - 1) has been computed. Its delta row goes to slot it & 1
+        // (still read by the compute warps after dO itself is dead), which dV(it - 1) has released as well.
+        mbar_wait(&bars[kDoEmpty], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[kDeltaFull + (it & 1)], kBlk * 4);
+        bulk_load_1d(sDelta + (it & 1) * kBlk, p.delta + row_off, kBlk * 4, &bars[kDeltaFull + (it & 1)]);
+        mbar_arrive_expect_tx(&bars[kDoFull], L::kTileBytes);
         for (int j = 0; j < kSub; ++j)
-          tma_load_4d(sDO + st * L::kTileBytes + j * kSubBytes, &tmap_do, &bars[kDoFull + st], j * 64, m * kBlk, head, batch);
-        bulk_load_1d(sDelta + st * kBlk, delta_src, kBlk * 4, &bars[kDoFull + st]);
+          tma_load_4d(sDO + j * kSubBytes, &tmap_do, &bars[kDoFull], j * 64, m * kBlk, head, batch);
+        if (++qs == kQStages) { qs = 0; qph ^= 1; }
       }
     }
   } else if (warp == 12) {
     // ========================================== MMA issuer =========================================
-    if (lane == 0 && T > 0) {
+    if (T > 0 && elect_one()) {
       constexpr uint32_t idesc_kk = make_idesc_f16(kBlk, kBlk, kBf16, false, false);  // S^T, dP^T
       constexpr uint32_t idesc_tn = make_idesc_f16(kBlk, D, kBf16, false, true);      // dV (TS), dK
       constexpr uint32_t idesc_nn = make_idesc_f16(kBlk, D, kBf16, true, true);       // dQ
@@ -307,57 +349,126 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_wait(&bars[kKvFull], 0);
       mbar_wait(&bars[kQFull + 0], 0);
       tcgen05_fence_after();
-      issue_kmajor(tmem_base + kTmemS, k_kmaj, q_kmaj);
+      issue_kmajor(tmem_base + kTmemS, k_kmaj, q_kmaj);  // S^T(0) = K Q(0)^T
       umma_commit(&bars[kSFull]);
+      mbar_wait(&bars[kDoFull], 0);
+      tcgen05_fence_after();
+      issue_kmajor(tmem_base + kTmemDP, v_kmaj, do_kmaj);  // dP^T(0) = V dO(0)^T
+      umma_commit(&bars[kDpFull]);
 
+      int qs = 0, qs_next = 1 % kQStages;
+      uint32_t qph_next = (kQStages == 1) ? 1u : 0u;
       for (int it = 0; it < T; ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
         const uint32_t par = it & 1;
-        const uint32_t st_off = st * L::kTileBytes;
+        const uint32_t q_off = qs * L::kTileBytes;
 
         // dV += P^T dO   (A = P^T from TMEM: k-steps 0-3 in columns [0,32), 4-7 in [64,96))
         mbar_wait(&bars[kPFull], par);
-        mbar_wait(&bars[kDoFull + st], ph);
         tcgen05_fence_after();
+        FA2_STAMP(2, it, 0);
 #pragma unroll
         for (int k = 0; k < kBlk / 16; ++k) {
           const uint32_t a_col = (k < 4) ? k * 8 : 64 + (k - 4) * 8;
-          umma_ts(tmem_base + kTmemDV, tmem_base + kTmemS + a_col, advance(do_mn, st_off + k * 2048), idesc_tn,
+          umma_ts(tmem_base + kTmemDV, tmem_base + kTmemS + a_col, advance(do_mn, k * 2048), idesc_tn,
                   (it > 0 || k > 0) ? 1u : 0u);
         }
-        // dP^T = V dO^T  (needs the dP/dQ columns back from the drain warps)
-        if (it > 0) {
-          mbar_wait(&bars[kDqEmpty], (it - 1) & 1);
-          tcgen05_fence_after();
-        }
-        issue_kmajor(tmem_base + kTmemDP, v_kmaj, advance(do_kmaj, st_off));
-        umma_commit(&bars[kDpFull]);
-        if constexpr (!L::kStagingAliasesDO) umma_commit(&bars[kDoEmpty + st]);
+        umma_commit(&bars[kDoEmpty]);  // dO(it) has now fed both dP(it) and dV(it)
+        FA2_STAMP(2, it, 1);
         // S^T(next) = K Q(next)^T
         if (it + 1 < T) {
-          mbar_wait(&bars[kQFull + (st ^ 1)], ((it + 1) >> 1) & 1);
+          mbar_wait(&bars[kQFull + qs_next], qph_next);
           tcgen05_fence_after();
-          issue_kmajor(tmem_base + kTmemS, k_kmaj, advance(q_kmaj, (st ^ 1) * L::kTileBytes));
+          issue_kmajor(tmem_base + kTmemS, k_kmaj, advance(q_kmaj, qs_next * L::kTileBytes));
           umma_commit(&bars[kSFull]);
         }
-        // dK += dS^T Q ; dQ = dS K
+        FA2_STAMP(2, it, 2);
+        // dQ = dS K, then dK += dS^T Q
         mbar_wait(&bars[kDsFull], par);
         tcgen05_fence_after();
+        FA2_STAMP(2, it, 3);
+        if constexpr (kFusedDq) {
+#pragma unroll
+          for (int k = 0; k < kBlk / 16; ++k) {
+            umma_ss(tmem_base + kTmemDP, advance(ds_mn, k * 2048), advance(k_mn, k * 2048), idesc_nn, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&bars[kDqFull]);
+        }
 #pragma unroll
         for (int k = 0; k < kBlk / 16; ++k) {
           const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
-          umma_ss(tmem_base + kTmemDK, advance(ds_kmaj, off), advance(q_mn, st_off + k * 2048), idesc_tn,
+          umma_ss(tmem_base + kTmemDK, advance(ds_kmaj, off), advance(q_mn, q_off + k * 2048), idesc_tn,
                   (it > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&bars[kQEmpty + st]);
-#pragma unroll
-        for (int k = 0; k < kBlk / 16; ++k) {
-          umma_ss(tmem_base + kTmemDP, advance(ds_mn, k * 2048), advance(k_mn, k * 2048), idesc_nn, k > 0 ? 1u : 0u);
+        umma_commit(&bars[kQEmpty + qs]);
+        FA2_STAMP(2, it, 4);
+        // dP^T(next) = V dO(next)^T  (needs dO(next) and the dP/dQ columns back from the drain warps)
+        if (it + 1 < T) {
+          mbar_wait(&bars[kDoFull], (it + 1) & 1);
+          if constexpr (kFusedDq) mbar_wait(&bars[kDqEmpty], par);
+          tcgen05_fence_after();
+          issue_kmajor(tmem_base + kTmemDP, v_kmaj, do_kmaj);
+          umma_commit(&bars[kDpFull]);
         }
-        umma_commit(&bars[kDqFull]);
+        FA2_STAMP(2, it, 5);
+        qs = qs_next;
+        if (++qs_next == kQStages) { qs_next = 0; qph_next ^= 1; }
       }
       umma_commit(&bars[kDkvFull]);
+    }
+  } else if (warp == 14) {
+    // ========================================= dQ reducer ==========================================
+    // One thread turns staged chunks into cp.reduce.async.bulk fp32 adds. Deterministic mode: the key blocks that
+    // see one query tile add in a fixed order, serialised by a ticket per tile.
+    if (kFusedDq && T > 0 && elect_one()) {
+      constexpr int kChunks = D / 32;
+      uint32_t n = 0;         // chunks issued so far (slot = n & 1, phase = (n >> 1) & 1)
+      uint32_t released = 0;  // chunks whose staging slot has been handed back to the drain warps
+      for (int it = 0; it < T; ++it) {
+        const int head = head_kv * group + it / m_count;
+        const int m = q_block_of(it);
+        float* gtile = p.dq_accum + ((static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / kBlk) + m) *
+                                        static_cast<int64_t>(kBlk) * D;
+        int* ticket = nullptr;
+        int my_turn = 0;
+        if (p.deterministic) {
+          ticket = p.dq_sem + (static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / kBlk) + m;
+          if (p.causal) {
+            // key blocks visible to query tile m: 0 .. n_last; they add in descending order
+            const int last_row = min(m * kBlk + kBlk, p.Sq) - 1;
+            const int n_last = min(n_kv_blocks - 1, (last_row + shift) / kBlk);
+            my_turn = n_last - nblk;
+          } else if (rotate) {
+            // rotated schedule: key block n reaches query tile m at step (m - n) mod n_q_blocks
+            const int top = min(m, n_kv_blocks - 1);
+            my_turn = (nblk <= m) ? (top - nblk) : (top + 1 + (n_kv_blocks - 1 - nblk));
+          } else {
+            my_turn = n_kv_blocks - 1 - nblk;
+          }
+        }
+        for (int c = 0; c < kChunks; ++c) {
+          const uint32_t slot = n & 1;
+          mbar_wait(&bars[kStageFull + slot], (n >> 1) & 1);
+          if (p.deterministic && c == 0) {
+            const long long start = clock64();
+            while (ld_acquire(ticket) != my_turn) {
+              if (clock64() - start > FA2_WATCHDOG_CYCLES) __trap();
+            }
+          }
+          bulk_reduce_add_f32(gtile + c * (kBlk * 32), smem + L::kStageOff + slot * L::kChunkBytes, L::kChunkBytes);
+          bulk_commit_group();
+          ++n;
+          bulk_wait_group_read<1>();  // every chunk but the one just issued has been read out of its slot
+          for (; released + 1 < n; ++released) mbar_arrive(&bars[kStageEmpty + (released & 1)]);
+        }
+        if (p.deterministic) {
+          bulk_wait_group<0>();  // every add of this tile is performed ...
+          for (; released < n; ++released) mbar_arrive(&bars[kStageEmpty + (released & 1)]);
+          __threadfence();
+          st_release(ticket, my_turn + 1);  // ... before the next key block may start its own
+        }
+        FA2_STAMP(3, it, 3);
+      }
+      bulk_wait_group<0>();
     }
   }
   } else if (warp < 8) {
@@ -370,91 +481,101 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const uint32_t tS = tmem_base + lane_sel + kTmemS + wg * 64;
     const uint32_t tP = tmem_base + lane_sel + kTmemS + wg * 64;  // P^T (16-bit) over this warpgroup's own S^T columns
     const uint32_t tDP = tmem_base + lane_sel + kTmemDP + wg * 64;
-    const float c = p.scale_log2;
+    const float2 neg_c2 = make_float2(-p.scale_log2, -p.scale_log2);
+    uint8_t* ds_sub = sDS + wg * kSubBytes;
 
+    int qs = 0;
+    uint32_t qph = 0;
     for (int it = 0; it < T; ++it) {
-      const int st = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
       const uint32_t par = it & 1;
       const int m = q_block_of(it);
       const int q0 = m * kBlk + wg * 64;  // first query column of this thread's slice
-      const float* lse_s = sLse + st * kBlk + wg * 64;
-      const float* delta_s = sDelta + st * kBlk + wg * 64;
+      const float4* lse_s = reinterpret_cast<const float4*>(sLse + qs * kBlk + wg * 64);
+      const float4* delta_s = reinterpret_cast<const float4*>(sDelta + (it & 1) * kBlk + wg * 64);
       const bool need_mask = (kv0 + kBlk > p.Sk) || (m * kBlk + kBlk > p.Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
 
-      // ---- P^T = exp2(S^T * c - LSE) ----
-      mbar_wait(&bars[kQFull + st], ph);  // LSE slice travels with Q
+      // ---- P^T = exp2(S^T * c - LSE) = exp2(-(LSE - S^T * c)) ----
+      if (r == 0) FA2_STAMP(wg, it, 0);
+      mbar_wait(&bars[kQFull + qs], qph);  // the LSE row travels with Q
       mbar_wait(&bars[kSFull], par);
       tcgen05_fence_after();
+      if (r == 0) FA2_STAMP(wg, it, 1);
       uint32_t su[2][32];
       tmem_ld_32x32b_x32(tS, su[0]);
       tmem_ld_32x32b_x32(tS + 32, su[1]);
       tmem_wait_ld();
-      float pf[64];
+      float2 pf[32];  // probabilities, fp32, pairs of neighbouring query columns
 #pragma unroll
       for (int j4 = 0; j4 < 16; ++j4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + j4 * 4);
-        const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = j4 * 4 + e;
-          // lse == -inf marks a fully masked query row: its probabilities are 0, not exp2(+inf)
-          const float neg_lse = (lv[e] == -INFINITY) ? -INFINITY : -lv[e];
-          pf[j] = ex2_approx(fmaf(__uint_as_float(su[j / 32][j % 32]), c, neg_lse));
-        }
+        const float4 l4 = lse_s[j4];
+        const int j = j4 * 4;
+        const float2 t0 = ffma2(make_float2(__uint_as_float(su[j / 32][j % 32]), __uint_as_float(su[j / 32][j % 32 + 1])),
+                                neg_c2, make_float2(l4.x, l4.y));
+        const float2 t1 = ffma2(make_float2(__uint_as_float(su[j / 32][j % 32 + 2]), __uint_as_float(su[j / 32][j % 32 + 3])),
+                                neg_c2, make_float2(l4.z, l4.w));
+        // a fully masked query row carries LSE = -inf: exp2(+inf) = inf here, replaced by 0 in the masked path below
+        // (such rows only occur in blocks that need masking)
+        pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
+        pf[j4 * 2 + 1] = make_float2(ex2_approx(-t1.x), ex2_approx(-t1.y));
       }
       if (need_mask) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int qi = q0 + j;
-          const bool ok = (kv < p.Sk) && (qi < p.Sq) && (!p.causal || kv <= qi + shift);
-          pf[j] = ok ? pf[j] : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          const int qi = q0 + 2 * j;
+          const bool row_ok = kv < p.Sk;
+          const bool ok0 = row_ok && (qi < p.Sq) && (!p.causal || kv <= qi + shift);
+          const bool ok1 = row_ok && (qi + 1 < p.Sq) && (!p.causal || kv <= qi + 1 + shift);
+          pf[j].x = ok0 ? pf[j].x : 0.f;
+          pf[j].y = ok1 ? pf[j].y : 0.f;
         }
       }
       {
         uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pk[j] = pack2<kBf16>(pf[2 * j], pf[2 * j + 1]);
+        for (int j = 0; j < 32; ++j) pk[j] = pack2<kBf16>(pf[j].x, pf[j].y);
         tmem_st_32x32b_x32(tP, pk);
         tmem_wait_st();
       }
       tcgen05_fence_before();
       mbar_arrive(&bars[kPFull]);
+      if (r == 0) FA2_STAMP(wg, it, 2);
 
       // ---- dS^T = P^T o (dP^T - delta) ----
-      mbar_wait(&bars[kDoFull + st], ph);  // delta slice travels with dO
+      mbar_wait(&bars[kDeltaFull + (it & 1)], (it >> 1) & 1);
       mbar_wait(&bars[kDpFull], par);
       tcgen05_fence_after();
-      uint8_t* ds_sub = sDS + wg * kSubBytes;
+      if (r == 0) FA2_STAMP(wg, it, 3);
+      uint32_t dpu[2][32];
+      tmem_ld_32x32b_x32(tDP, dpu[0]);
+      tmem_wait_ld();
+      tmem_ld_32x32b_x32(tDP + 32, dpu[1]);  // in flight while the first half is processed
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t dpu[32];
-        tmem_ld_32x32b_x32(tDP + half * 32, dpu);
-        tmem_wait_ld();
+        if (half == 1) tmem_wait_ld();
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
-          float ds[8];
+          uint32_t w[4];
 #pragma unroll
           for (int e4 = 0; e4 < 2; ++e4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(delta_s + half * 32 + c16 * 8 + e4 * 4);
-            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c16 * 8 + e4 * 4 + e;
-              ds[e4 * 4 + e] = pf[half * 32 + j] * (__uint_as_float(dpu[j]) - dv[e]);
-            }
+            const float4 d4 = delta_s[half * 8 + c16 * 2 + e4];
+            const int j = c16 * 8 + e4 * 4;
+            const float2 x0 = fsub2(make_float2(__uint_as_float(dpu[half][j]), __uint_as_float(dpu[half][j + 1])),
+                                    make_float2(d4.x, d4.y));
+            const float2 x1 = fsub2(make_float2(__uint_as_float(dpu[half][j + 2]), __uint_as_float(dpu[half][j + 3])),
+                                    make_float2(d4.z, d4.w));
+            const float2 s0 = fmul2(pf[half * 16 + c16 * 4 + e4 * 2], x0);
+            const float2 s1 = fmul2(pf[half * 16 + c16 * 4 + e4 * 2 + 1], x1);
+            w[e4 * 2] = pack2<kBf16>(s0.x, s0.y);
+            w[e4 * 2 + 1] = pack2<kBf16>(s1.x, s1.y);
           }
-          uint4 v;
-          v.x = pack2<kBf16>(ds[0], ds[1]);
-          v.y = pack2<kBf16>(ds[2], ds[3]);
-          v.z = pack2<kBf16>(ds[4], ds[5]);
-          v.w = pack2<kBf16>(ds[6], ds[7]);
-          *reinterpret_cast<uint4*>(ds_sub + sw128_offset(r, half * 4 + c16)) = v;
+          *reinterpret_cast<uint4*>(ds_sub + sw128_offset(r, half * 4 + c16)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
       mbar_arrive(&bars[kDsFull]);
+      if (r == 0) FA2_STAMP(wg, it, 4);
+      if (++qs == kQStages) { qs = 0; qph ^= 1; }
     }
 
     // ---- epilogue: dK * scale, dV -> smem (the K / V tiles are dead once every MMA retired) -> TMA store ----
@@ -503,94 +624,40 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
   } else {
     // ========================================== dQ drain ===========================================
+    // TMEM -> registers (frees the dP/dQ columns at once) -> 16 KB staging chunks -> the reducer thread.
     reg_alloc<kRegsMath>();
     const int r = threadIdx.x & 127;  // query row inside the block == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tDQ = tmem_base + lane_sel + kTmemDP;
-    const bool leader = (r == 0);
+    constexpr int kChunks = D / 32;
+    uint32_t n = 0;  // running chunk counter: slot = n & 1
 
-    for (int it = 0; it < T; ++it) {
-      const int st = it & 1;
+    for (int it = 0; kFusedDq && it < T; ++it) {
       const uint32_t par = it & 1;
-      const int head = head_kv * group + it / m_count;
-      const int m = q_block_of(it);
-      uint8_t* stage = L::kStagingAliasesDO ? (sDO + st * L::kTileBytes) : (smem + L::kStageOff);
-      float* gtile = p.dq_accum + ((static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / kBlk) + m) *
-                                      static_cast<int64_t>(kBlk) * D;
-
       mbar_wait(&bars[kDqFull], par);
       tcgen05_fence_after();
-      uint32_t acc[kPanels][2][32];
+      if (r == 0) FA2_STAMP(3, it, 0);
+      uint32_t acc[kChunks][32];
 #pragma unroll
-      for (int pn = 0; pn < kPanels; ++pn) {
-        tmem_ld_32x32b_x32(tDQ + pn * 64, acc[pn][0]);
-        tmem_ld_32x32b_x32(tDQ + pn * 64 + 32, acc[pn][1]);
-      }
+      for (int c = 0; c < kChunks; ++c) tmem_ld_32x32b_x32(tDQ + c * 32, acc[c]);
       tmem_wait_ld();
       tcgen05_fence_before();
       mbar_arrive(&bars[kDqEmpty]);  // dP^T(next) may overwrite these columns now
-
-      int* ticket = nullptr;
-      int my_turn = 0;
-      if (p.deterministic) {
-        ticket = p.dq_sem + (static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / kBlk) + m;
-        if (p.causal) {
-          // key blocks visible to query tile m: 0 .. n_last; they add in descending order
-          const int last_row = min(m * kBlk + kBlk, p.Sq) - 1;
-          const int n_last = min(n_kv_blocks - 1, (last_row + shift) / kBlk);
-          my_turn = n_last - nblk;
-        } else if (rotate) {
-          // rotated schedule: key block n reaches query tile m at step (m - n) mod n_q_blocks
-          const int top = min(m, n_kv_blocks - 1);
-          my_turn = (nblk <= m) ? (top - nblk) : (top + 1 + (n_kv_blocks - 1 - nblk));
-        } else {
-          my_turn = n_kv_blocks - 1 - nblk;
-        }
-      }
-
+      if (r == 0) FA2_STAMP(3, it, 1);
 #pragma unroll
-      for (int pn = 0; pn < kPanels; ++pn) {
-        // staging must be free of the previous bulk reduction's reads
-        if (pn > 0 || !L::kStagingAliasesDO) {
-          if (leader) bulk_wait_group_read<0>();
-          named_bar_sync(2, 128);
-        }
+      for (int c = 0; c < kChunks; ++c, ++n) {
+        const uint32_t slot = n & 1;
+        mbar_wait(&bars[kStageEmpty + slot], ((n >> 1) & 1) ^ 1);
+        uint8_t* row = smem + L::kStageOff + slot * L::kChunkBytes + r * 128;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            uint4 v;
-            v.x = acc[pn][h2][c4 * 4 + 0];
-            v.y = acc[pn][h2][c4 * 4 + 1];
-            v.z = acc[pn][h2][c4 * 4 + 2];
-            v.w = acc[pn][h2][c4 * 4 + 3];
-            const uint32_t chunk = h2 * 8 + c4;  // 16-byte chunk inside the 256-byte row
-            *reinterpret_cast<uint4*>(stage + r * 256 + ((chunk ^ (r & 7)) << 4)) = v;
-          }
+        for (int pc = 0; pc < 8; ++pc) {
+          *reinterpret_cast<uint4*>(row + ((pc ^ (r & 7)) << 4)) =
+              make_uint4(acc[c][pc * 4], acc[c][pc * 4 + 1], acc[c][pc * 4 + 2], acc[c][pc * 4 + 3]);
         }
         fence_proxy_async_smem();
-        named_bar_sync(3, 128);
-        if (leader) {
-          if (p.deterministic && pn == 0) {
-            const long long start = clock64();
-            while (ld_acquire(ticket) != my_turn) {
-              if (clock64() - start > FA2_WATCHDOG_CYCLES) __trap();
-            }
-          }
-          bulk_reduce_add_f32(gtile + pn * (kBlk * 64), stage, L::kPanelBytes);
-          bulk_commit_group();
-        }
+        mbar_arrive(&bars[kStageFull + slot]);
       }
-      if (leader) {
-        if (p.deterministic) {
-          bulk_wait_group<0>();
-          __threadfence();
-          st_release(ticket, my_turn + 1);
-        } else {
-          bulk_wait_group_read<0>();
-        }
-        if constexpr (L::kStagingAliasesDO) mbar_arrive(&bars[kDoEmpty + st]);
-      }
+      if (r == 0) FA2_STAMP(3, it, 2);
     }
   }
 
@@ -598,15 +665,15 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   __syncthreads();
   if (warp == 12) {
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<512>(0u);
   }
 }
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kFusedDq>
 static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                 const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
                                 const BwdParams& p, cudaStream_t stream) {
-  auto kernel = fa2_bwd_kernel<D, kBf16>;
+  auto kernel = fa2_bwd_kernel<D, kBf16, kFusedDq>;
   constexpr int smem = BwdSmem<D>::kBytes;
   static bool configured[64] = {};
   int dev = 0;
@@ -621,59 +688,73 @@ static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
   return cudaGetLastError();
 }
 
-cudaError_t launch_bwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                       const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p,
-                       cudaStream_t stream) {
-  if (D == 128) return bf16 ? launch_bwd_t<128, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)
-                            : launch_bwd_t<128, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
-  if (D == 64) return bf16 ? launch_bwd_t<64, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)
-                           : launch_bwd_t<64, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
+cudaError_t launch_bwd(int D, bool bf16, bool fused_dq, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
+                       const BwdParams& p, cudaStream_t stream) {
+#define FA2_BWD_CASE(DD, BF, FU) \
+  if (D == DD && bf16 == BF && fused_dq == FU) return launch_bwd_t<DD, BF, FU>(tq, tk, tv, tdo, tdk, tdv, p, stream);
+  FA2_BWD_CASE(128, true, true) FA2_BWD_CASE(128, true, false) FA2_BWD_CASE(128, false, true) FA2_BWD_CASE(128, false, false)
+  FA2_BWD_CASE(64, true, true) FA2_BWD_CASE(64, true, false) FA2_BWD_CASE(64, false, true) FA2_BWD_CASE(64, false, false)
+#undef FA2_BWD_CASE
   return cudaErrorInvalidValue;
 }
 
 // =================================================================================================
 // dQ accumulator -> dQ
 // =================================================================================================
+// One CTA per 64 accumulator rows: reads the chunked / swizzled layout with coalesced float4 loads (128 contiguous
+// bytes per row and chunk), un-swizzles through shared memory and writes rows of the caller's [B, Sq, Hq, D]
+// tensor in 16-byte pieces.
+template <int D>
 __global__ void __launch_bounds__(256) fa2_dq_convert_kernel(const DqConvertParams p) {
-  // one thread per 16-byte chunk (4 floats) of the accumulator
-  const int chunks_per_row = p.D / 4;
-  const int64_t total = static_cast<int64_t>(p.B) * p.Hq * p.Sq * chunks_per_row;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int cd = static_cast<int>(idx % chunks_per_row);  // logical chunk along D
-    int64_t rest = idx / chunks_per_row;
-    const int head = static_cast<int>(rest % p.Hq);
-    rest /= p.Hq;
-    const int row = static_cast<int>(rest % p.Sq);
-    const int batch = static_cast<int>(rest / p.Sq);
-    const int tile = row / 128, r = row % 128;
-    const int panel = cd / 16, chunk = cd % 16;
-    const int64_t tile_base = ((static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / 128) + tile) * 128LL * p.D;
-    const float* src = p.dq_accum + tile_base + static_cast<int64_t>(panel) * (128 * 64) + r * 64 + ((chunk ^ (r & 7)) << 2);
-    float4 v = *reinterpret_cast<const float4*>(src);
-    v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-    const int64_t dst = batch * p.dq_strides[0] + head * p.dq_strides[1] + static_cast<int64_t>(row) * p.dq_strides[2] + cd * 4;
+  constexpr int kRows = 64;
+  constexpr int kPitch = D + 4;  // floats; keeps both the transposing writes and the row reads conflict-free
+  __shared__ __align__(16) float tile[kRows * kPitch];
+  const int half = blockIdx.x & 1, tile_idx = blockIdx.x >> 1;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int row0 = tile_idx * 128 + half * kRows;
+  if (row0 >= p.Sq) return;
+  const float* src = p.dq_accum + ((static_cast<int64_t>(batch) * p.Hq + head) * (p.sq_pad / 128) + tile_idx) * 128LL * D;
+  // accumulator: [chunk (32 columns)][row][8 pieces of 16 B], piece p of row r holds logical piece p ^ (r & 7)
+  for (int idx = threadIdx.x; idx < (D / 32) * kRows * 8; idx += 256) {
+    const int pc = idx & 7, r = (idx >> 3) & (kRows - 1), c = idx / (8 * kRows);
+    const int row_in_tile = half * kRows + r;
+    const float4 v = *reinterpret_cast<const float4*>(src + ((c * 128 + row_in_tile) * 8 + pc) * 4);
+    const int col = c * 32 + ((pc ^ (row_in_tile & 7)) << 2);
+    *reinterpret_cast<float4*>(&tile[r * kPitch + col]) = make_float4(v.x * p.scale, v.y * p.scale, v.z * p.scale, v.w * p.scale);
+  }
+  __syncthreads();
+  const int esize = (p.out_dtype == 32) ? 4 : 2;
+  const int per16 = 16 / esize;                 // elements per 16-byte piece
+  const int pieces_per_row = D / per16;
+  uint8_t* out = reinterpret_cast<uint8_t*>(p.dq);
+  for (int idx = threadIdx.x; idx < kRows * pieces_per_row; idx += 256) {
+    const int rr = idx / pieces_per_row, pc = idx % pieces_per_row;
+    const int row = row0 + rr;
+    if (row >= p.Sq) continue;
+    const float* t = &tile[rr * kPitch + pc * per16];
+    const int64_t dst = (batch * p.dq_strides[0] + head * p.dq_strides[1] + static_cast<int64_t>(row) * p.dq_strides[2] + pc * per16) * esize;
     if (p.out_dtype == 32) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dq) + dst) = v;
-    } else if (p.out_dtype == 17) {
-      uint2 o;
-      o.x = pack2<true>(v.x, v.y);
-      o.y = pack2<true>(v.z, v.w);
-      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dq) + dst) = o;
+      *reinterpret_cast<float4*>(out + dst) = *reinterpret_cast<const float4*>(t);
     } else {
-      uint2 o;
-      o.x = pack2<false>(v.x, v.y);
-      o.y = pack2<false>(v.z, v.w);
-      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dq) + dst) = o;
+      const float4 a = *reinterpret_cast<const float4*>(t);
+      const float4 b = *reinterpret_cast<const float4*>(t + 4);
+      uint4 o;
+      if (p.out_dtype == 17) {
+        o = make_uint4(pack2<true>(a.x, a.y), pack2<true>(a.z, a.w), pack2<true>(b.x, b.y), pack2<true>(b.z, b.w));
+      } else {
+        o = make_uint4(pack2<false>(a.x, a.y), pack2<false>(a.z, a.w), pack2<false>(b.x, b.y), pack2<false>(b.z, b.w));
+      }
+      *reinterpret_cast<uint4*>(out + dst) = o;
     }
   }
 }
 
 cudaError_t launch_dq_convert(const DqConvertParams& p, cudaStream_t stream) {
-  const int64_t total = static_cast<int64_t>(p.B) * p.Hq * p.Sq * (p.D / 4);
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  fa2_dq_convert_kernel<<<blocks, 256, 0, stream>>>(p);
+  dim3 grid(2 * (p.sq_pad / 128), p.Hq, p.B);
+  if (p.D == 128) fa2_dq_convert_kernel<128><<<grid, 256, 0, stream>>>(p);
+  else if (p.D == 64) fa2_dq_convert_kernel<64><<<grid, 256, 0, stream>>>(p);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -51,9 +51,27 @@ struct BwdParams {
   int causal;
   int deterministic;
 };
-cudaError_t launch_bwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                       const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p,
-                       cudaStream_t stream);
+// fused_dq = true : dK, dV and dQ partial sums (atomic mode; 5 products per block pair)
+// fused_dq = false: dK, dV only (deterministic mode; dQ comes from launch_bwd_dq)
+cudaError_t launch_bwd(int D, bool bf16, bool fused_dq, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
+                       const BwdParams& p, cudaStream_t stream);
+
+// dQ kernel of the deterministic backward (bwd_dq_sm100.cu): one CTA per 128-row query block, fixed key-block order
+struct DqParams {
+  const float* lse;    // [B, Hq, lse_stride] log2 domain
+  const float* delta;  // [B, Hq, lse_stride]
+  void* dq;            // [B, Sq, Hq, D] (used directly when dq_is_16bit == 0, otherwise through the tensor map)
+  int64_t dq_strides[3];  // batch, head, seq (elements)
+  int dq_is_16bit;     // 1: dq has the input dtype (TMA store), 0: dq is fp32 (vector stores)
+  int B, Hq, Hkv, Sq, Sk;
+  int lse_stride;
+  float softmax_scale;
+  float scale_log2;
+  int causal;
+};
+cudaError_t launch_bwd_dq(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                          const CUtensorMap& tdo, const CUtensorMap& tdq, const DqParams& p, cudaStream_t stream);
 
 struct DqConvertParams {
   const float* dq_accum;  // as written by the backward kernel
@@ -82,5 +100,10 @@ struct ProbeParams {
 };
 cudaError_t launch_probe(bool bf16, const CUtensorMap& ta, const CUtensorMap& tb, const ProbeParams& p,
                          cudaStream_t stream);
+
+#ifdef FA2_TRACE
+cudaError_t fetch_fwd_trace(long long* host, size_t n);
+cudaError_t fetch_bwd_trace(long long* host, size_t n);
+#endif
 
 }  // namespace fa2

@@ -20,6 +20,18 @@
 
 namespace fa2 {
 
+#ifdef FA2_TRACE
+// Debug build only (make TRACE=1): clock64() stamps of one CTA's pipeline events, [role][iteration][event].
+__device__ long long g_fwd_trace[3 * 64 * 8];
+#define FA2_STAMP(role, it, ev)                                                                          \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 64)                              \
+      g_fwd_trace[((role) * 64 + (it)) * 8 + (ev)] = clock64();                                          \
+  } while (0)
+#else
+#define FA2_STAMP(role, it, ev) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kBM = 128;  // query rows per tile (= TMEM lanes)
@@ -120,7 +132,12 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // This CTA allocated all 512 columns, so the allocation starts at lane 0 / column 0. Using the literal 0 (after
+  // checking it) keeps every tcgen05 address provably warp-uniform: ptxas then feeds UTCHMMA / LDTM / STTM from
+  // uniform registers directly instead of wrapping each one in an ELECT + R2UR.BROADCAST "waterfall" (which cost
+  // ~100 issue cycles per MMA and made the single issuing thread the bottleneck - profiles/r01_fwd_hot.txt).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   // setmaxnreg at the top of each role branch (ptxas widens the budget only for dominated code):
   // pool = 384 threads x 168 launch registers = 64512 = 2 softmax warpgroups x 128 x 208 + 1 issue warpgroup x 128 x 88
@@ -128,7 +145,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     reg_dealloc<88>();
   if (warp == 9) {
     // ======================================= TMA producer =======================================
-    if (lane == 0 && nblk_max > 0) {
+    if (nblk_max > 0 && elect_one()) {
       const int n_q_tiles = (row0 + kBM < p.Sq) ? 2 : 1;
       mbar_arrive_expect_tx(q_full, n_q_tiles * L::kTileBytes);
       for (int t = 0; t < n_q_tiles; ++t)
@@ -149,7 +166,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
   } else if (warp == 8) {
     // ======================================== MMA issuer ========================================
-    if (lane == 0 && nblk_max > 0) {
+    if (nblk_max > 0 && elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kBM, kBN, kBf16, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(kBM, D, kBf16, false, true);
       const int nblk[2] = {nblk0, nblk1};
@@ -178,6 +195,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tcgen05_fence_after();
+#pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (nblk[t] > 0) {
           issue_qk(t, 0);
@@ -193,21 +211,27 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const uint32_t phn = ((i + 1) / kStages) & 1;
         bool next_k_ready = false;
         mbar_wait(&v_full[s], ph);
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (i >= nblk[t]) continue;
-          mbar_wait(&p_full[t], i & 1);
-          tcgen05_fence_after();
-          issue_pv(t, s, i > 0);
-          if (i + 1 < nblk[t]) {
-            if (!next_k_ready) {
-              mbar_wait(&k_full[sn], phn);
-              tcgen05_fence_after();
-              next_k_ready = true;
+          if (i < nblk[t]) {
+            mbar_wait(&p_full[t], i & 1);
+            tcgen05_fence_after();
+            FA2_STAMP(2, i, t * 4 + 0);
+            issue_pv(t, s, i > 0);
+            FA2_STAMP(2, i, t * 4 + 1);
+            if (i + 1 < nblk[t]) {
+              if (!next_k_ready) {
+                mbar_wait(&k_full[sn], phn);
+                tcgen05_fence_after();
+                next_k_ready = true;
+              }
+              FA2_STAMP(2, i, t * 4 + 2);
+              issue_qk(t, sn);
+              umma_commit(&s_full[t]);
+              FA2_STAMP(2, i, t * 4 + 3);
+            } else {
+              umma_commit(&o_full[t]);
             }
-            issue_qk(t, sn);
-            umma_commit(&s_full[t]);
-          } else {
-            umma_commit(&o_full[t]);
           }
         }
         umma_commit(&v_empty[s]);
@@ -233,13 +257,16 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     float l = 0.f;
 
     for (int i = 0; i < nblk; ++i) {
+      if (r == 0) FA2_STAMP(t, i, 0);
       mbar_wait(&s_full[t], i & 1);
       tcgen05_fence_after();
+      if (r == 0) FA2_STAMP(t, i, 1);
 
       uint32_t su[kBN / 32][32];  // raw fp32 bits of this thread's score row
 #pragma unroll
       for (int cidx = 0; cidx < kBN / 32; ++cidx) tmem_ld_32x32b_x32(tS + cidx * 32, su[cidx]);
       tmem_wait_ld();
+      if (r == 0) FA2_STAMP(t, i, 2);
       float s[kBN];
 #pragma unroll
       for (int j = 0; j < kBN; ++j) s[j] = __uint_as_float(su[j / 32][j % 32]);
@@ -283,6 +310,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       l *= alpha;
 
+      if (r == 0) FA2_STAMP(t, i, 3);
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float l0 = 0.f, l1 = 0.f;
       uint32_t pk[kBN / 64][32];
@@ -296,10 +324,12 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       l += l0 + l1;
 #pragma unroll
+      if (r == 0) FA2_STAMP(t, i, 4);
       for (int cidx = 0; cidx < kBN / 64; ++cidx) tmem_st_32x32b_x32(tS + cidx * 32, pk[cidx]);
       tmem_wait_st();
       tcgen05_fence_before();
       mbar_arrive(&p_full[t]);
+      if (r == 0) FA2_STAMP(t, i, 5);
     }
 
     // ------------------------------ epilogue: O / l -> smem -> TMA store ---------------------------
@@ -357,7 +387,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   __syncthreads();
   if (warp == 8) {
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<512>(0u);
   }
 }
 
@@ -381,6 +411,12 @@ static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
   kernel<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, p);
   return cudaGetLastError();
 }
+
+#ifdef FA2_TRACE
+cudaError_t fetch_fwd_trace(long long* host, size_t n) {
+  return cudaMemcpyFromSymbol(host, g_fwd_trace, n * sizeof(long long));
+}
+#endif
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {

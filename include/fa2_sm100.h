@@ -8,8 +8,8 @@
  *   fa2_sm100_bwd_delta      <- `_compute_delta[grid](...)`    src/backward/caller.py:94-114
  *   fa2_sm100_bwd            <- `_bwd_kernel[grid](...)`       src/backward/caller.py:118-160
  *   fa2_sm100_dq_convert     <- the fp32 `dq` the reference allocates at src/backward/caller.py:86
- *                               (our dQ accumulator is an opaque tile-swizzled workspace; this call turns it
- *                               into the caller-visible [B, Sq, Hq, D] tensor)
+ *                               (in the atomic modes our dQ accumulator is an opaque tile-swizzled workspace; this
+ *                               call turns it into the caller-visible [B, Sq, Hq, D] tensor)
  *
  * Conventions shared by every call
  *   - tensors are device pointers; q/o/do are [B, Sq, Hq, D], k/v/dk/dv are [B, Sk, Hkv, D] with a contiguous
@@ -39,11 +39,16 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 2
+#define FA2_SM100_ABI_VERSION 3
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
 #define FA2_DTYPE_FP32 32
+
+/* how dQ is summed over key blocks (the `deterministic` argument) */
+#define FA2_DQ_ATOMIC 0         /* fused kernel, fp32 adds into an accumulator in arrival order (fast mode) */
+#define FA2_DQ_DETERMINISTIC 1  /* separate dQ kernel, one CTA per query block, fixed key-block order, no atomics */
+#define FA2_DQ_FUSED_ORDERED 2  /* fused kernel, adds serialised per query tile by a ticket (bit-repeatable, slowest) */
 
 #define FA2_E_UNSUPPORTED_HEAD_DIM (-1)
 #define FA2_E_UNSUPPORTED_DTYPE (-2)
@@ -71,24 +76,27 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
                         const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride,
                         int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Bytes of scratch fa2_sm100_bwd needs: the fp32 dQ accumulator plus (deterministic mode) one int per
- * (batch, head, 128-row query tile). The workspace must be 16-byte aligned. */
+/* Bytes of scratch fa2_sm100_bwd needs: 0 in FA2_DQ_DETERMINISTIC mode; otherwise the fp32 dQ accumulator plus one
+ * int per (batch, head, 128-row query tile). The workspace must be 16-byte aligned. */
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic);
 
-/* dK, dV (input dtype, [B, Sk, Hkv, D]) and the fp32 dQ accumulator inside `workspace`.
- * The workspace must be all zero on entry: pass it to fa2_sm100_bwd_delta (same stream) or clear it yourself.
- * deterministic != 0: contributions to each dQ tile are added in a fixed key-block order, results are
- * bit-identical run to run; deterministic == 0: same adds in arrival order (fast mode). */
+/* dQ ([B, Sq, Hq, D], `dq_dtype` = the input dtype or 32 for fp32 as the reference allocates it at
+ * src/backward/caller.py:86), dK and dV (input dtype, [B, Sk, Hkv, D], GQA head groups already summed).
+ * `deterministic` selects the dQ path (FA2_DQ_*). Modes 0 and 2 need `workspace`, all zero on entry: pass it to
+ * fa2_sm100_bwd_delta (same stream) or clear it yourself. Mode 1 ignores `workspace`. Results of modes 1 and 2 are
+ * bit-identical run to run. */
 int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
                   const float* lse, const float* delta,
-                  void* dk, void* dv, void* workspace, size_t workspace_bytes,
+                  void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes,
                   int B, int Hq, int Hkv, int Sq, int Sk, int D,
                   const int64_t do_strides[3], const int64_t q_strides[3], const int64_t k_strides[3],
-                  const int64_t v_strides[3], const int64_t dk_strides[3], const int64_t dv_strides[3],
-                  int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype,
+                  const int64_t v_strides[3], const int64_t dq_strides[3], const int64_t dk_strides[3],
+                  const int64_t dv_strides[3],
+                  int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype,
                   void* stream);
 
-/* dq[b, i, h, :] = softmax_scale * accumulator[b, h, i, :], written as `out_dtype` (16, 17 or 32). */
+/* dq[b, i, h, :] = softmax_scale * accumulator[b, h, i, :], written as `out_dtype` (16, 17 or 32). Called by
+ * fa2_sm100_bwd itself in modes 0 and 2; exported for callers that keep several accumulators in flight. */
 int fa2_sm100_dq_convert(const void* workspace, void* dq,
                          int B, int Hq, int Sq, int D,
                          const int64_t dq_strides[3], float softmax_scale, int out_dtype, void* stream);

@@ -30,16 +30,18 @@ def test_library_exports_every_declared_symbol():
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/fa2_sm100.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.fa2_sm100_version() == 2
+    assert lib.fa2_sm100_version() == 3
 
 
 def test_workspace_size_formula():
     from fa2_triton_b200 import _lib
     lib = _lib.load()
-    # fp32 accumulator over Sq padded to 128 + one ticket per (b, h, tile), 16-byte rounded
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1) == 4 * 32 * 4096 * 128 * 4 + 4 * 32 * 32 * 4
-    assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 1000, 1000, 64, 0) == 1024 * 64 * 4 + 32
+    # atomic / fused-ordered: fp32 accumulator over Sq padded to 128 + one ticket per (b, h, tile), 16-byte rounded
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 0) == 4 * 32 * 4096 * 128 * 4 + 4 * 32 * 32 * 4
+    assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 1000, 1000, 64, 2) == 1024 * 64 * 4 + 32
     assert lib.fa2_sm100_bwd_workspace_bytes(0, 1, 1, 1, 64, 0) == 0
+    # deterministic: dQ has its own kernel, nothing to accumulate into
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1) == 0
 
 
 def test_argument_errors_need_no_gpu():

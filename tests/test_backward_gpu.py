@@ -47,8 +47,23 @@ def test_backward_matches_oracle(Sq, Sk, D, causal, dtype):
 
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("D", [64, 128])
-def test_backward_atomic_mode_matches_oracle(D, causal):
-    run_case(2, 640, 640, 3, 3, D, causal, torch.bfloat16, deterministic=False)
+@pytest.mark.parametrize("mode", [0, 2])  # 0: atomic fast mode, 2: fused kernel with ticket-ordered adds
+def test_backward_fused_modes_match_oracle(D, causal, mode):
+    run_case(2, 640, 640, 3, 3, D, causal, torch.bfloat16, deterministic=mode)
+    run_case(1, 113, 203, 2, 2, D, causal, torch.bfloat16, deterministic=mode)
+
+
+def test_backward_fp32_dq_like_the_reference():
+    """`_flash_attn_backward` returns dq in fp32 by default (src/backward/caller.py:86), in every dQ mode."""
+    q, k, v, do = generate_test_data(2, 300, 300, 4, 2, 128, torch.bfloat16, DEV, 8)
+    o, lse, scale, _ = fa2._flash_attn_forward(q, k, v, None, None, 0.0, True, None, None)
+    ref = er.fwd_bwd(q, k, v, do, causal=True)
+    for mode in (0, 1, 2):
+        dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, None, o, lse, 0.0, True, scale, None, deterministic=mode)
+        assert dq.dtype == torch.float32 and dk.dtype == torch.bfloat16
+        assert_close_16("dQ", dq, ref[1])
+        assert_close_16("dK", dk, ref[2])
+        assert_close_16("dV", dv, ref[3])
 
 
 @pytest.mark.parametrize("Hq,Hkv", [(8, 2), (4, 1)])
@@ -66,15 +81,16 @@ def test_backward_fully_masked_rows_have_zero_dq():
     assert_close_16("dV", dv, ref[3])
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("D", [64, 128])
-def test_deterministic_mode_is_bit_repeatable(D, causal):
+def test_deterministic_mode_is_bit_repeatable(D, causal, mode):
     """Intent of the reference's tests/test_repeatability.py:18-53 (10 repeats, identical results), checked on the
     full tensors instead of masked checksums."""
     q, k, v, do = generate_test_data(2, 1024, 1024, 4, 4, D, torch.bfloat16, DEV, 4)
-    first = ours_fwd_bwd(q, k, v, do, causal, deterministic=True)
+    first = ours_fwd_bwd(q, k, v, do, causal, deterministic=mode)
     for _ in range(9):
-        again = ours_fwd_bwd(q, k, v, do, causal, deterministic=True)
+        again = ours_fwd_bwd(q, k, v, do, causal, deterministic=mode)
         for a, b in zip(first, again):
             assert torch.equal(a, b)
     assert not any(torch.isnan(t).any() for t in first)
