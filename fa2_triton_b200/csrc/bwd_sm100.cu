@@ -515,8 +515,9 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 neg_c2, make_float2(l4.z, l4.w));
         // a fully masked query row carries LSE = -inf: exp2(+inf) = inf here, replaced by 0 in the masked path below
         // (such rows only occur in blocks that need masking)
+        // one pair on the MUFU, one on the FMA pipes (ex2_emul2_neg): halves the MUFU time of this phase
         pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
-        pf[j4 * 2 + 1] = make_float2(ex2_approx(-t1.x), ex2_approx(-t1.y));
+        pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
       }
       if (need_mask) {
 #pragma unroll

@@ -15,6 +15,8 @@
 //   warps 10-11: idle (keep the third warpgroup whole for setmaxnreg)
 // TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,256+D) | O1 [256+D,256+2D).
 //   P_t (16-bit, 64 columns) overwrites the first half of S_t once the owning thread has read its row.
+#include <type_traits>
+
 #include "fa2_kernels.cuh"
 #include "ptx.cuh"
 
@@ -38,6 +40,18 @@ constexpr int kBM = 128;  // query rows per tile (= TMEM lanes)
 constexpr int kBN = 128;  // key rows per block
 constexpr int kFwdThreads = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between rescales
+// Of every FA2_FWD_EMUL_DEN probabilities, FA2_FWD_EMUL_NUM are exponentiated on the FMA pipes (ex2_emul) and the rest
+// on the MUFU. Measured issue costs per warp instruction and scheduler (scripts/micro/pipe_rates.cu): MUFU.EX2 8 cycles,
+// FFMA / FADD / IMAD 1, FMNMX / F2FP 2 - an emulated exponential is 8 instructions, so about a quarter of them
+// would balance the pipes on paper. Measured on B200 (B=4,H=32,S=4096,D=128 causal): 0/4 -> 0.567 ms, 1/4 -> 0.591,
+// 1/3 -> 0.616, 1/2 -> 0.651: with one softmax warp per scheduler the phase is latency-bound, not MUFU-bound, and the
+// extra dependent instructions cost more than the MUFU slots they free. Default: off.
+#ifndef FA2_FWD_EMUL_NUM
+#define FA2_FWD_EMUL_NUM 0
+#endif
+#ifndef FA2_FWD_EMUL_DEN
+#define FA2_FWD_EMUL_DEN 4
+#endif
 
 template <int D>
 struct FwdSmem {
@@ -211,6 +225,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const uint32_t phn = ((i + 1) / kStages) & 1;
         bool next_k_ready = false;
         mbar_wait(&v_full[s], ph);
+        if (i + 1 < nblk_max) {  // K(i+1) is usually there long before P(i): take that wait off the P -> S chain
+          mbar_wait(&k_full[sn], phn);
+          next_k_ready = true;
+        }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (i < nblk[t]) {
@@ -280,15 +298,15 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int j = 0; j < kBN; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
       }
 
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      float mx[8];
 #pragma unroll
-      for (int j = 4; j < kBN; j += 4) {
-        mx0 = fmaxf(mx0, s[j]);
-        mx1 = fmaxf(mx1, s[j + 1]);
-        mx2 = fmaxf(mx2, s[j + 2]);
-        mx3 = fmaxf(mx3, s[j + 3]);
+      for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[j], s[j + 8]);
+#pragma unroll
+      for (int j = 16; j < kBN; j += 16) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], fmaxf(s[j + e], s[j + e + 8]));
       }
-      const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+      const float mb = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
 
       // lazy rescale: only move the reference max when the block max exceeds it by > 2^8
       const bool need = mb > m_ref + kRescaleThreshold;
@@ -312,16 +330,29 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
       if (r == 0) FA2_STAMP(t, i, 3);
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-      float l0 = 0.f, l1 = 0.f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[kBN / 64][32];
+      auto exp_block = [&](auto emulate) {
 #pragma unroll
-      for (int j = 0; j < kBN; j += 2) {
-        const float p0 = ex2_approx(fmaf(s[j], c, neg_m));
-        const float p1 = ex2_approx(fmaf(s[j + 1], c, neg_m));
-        l0 += p0;
-        l1 += p1;
-        pk[j / 64][(j / 2) % 32] = pack2<kBf16>(p0, p1);
-      }
+        for (int j = 0; j < kBN; j += 2) {
+          float pr[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float x = fmaf(s[j + e], c, neg_m);
+            if (decltype(emulate)::value && ((j + e) % FA2_FWD_EMUL_DEN) < FA2_FWD_EMUL_NUM) {
+              pr[e] = ex2_emul(x);
+            } else {
+              pr[e] = ex2_approx(x);
+            }
+            ls[(j + e) % 4] += pr[e];
+          }
+          pk[j / 64][(j / 2) % 32] = pack2<kBf16>(pr[0], pr[1]);
+        }
+      };
+      // masked blocks keep every exponential on the MUFU (exact 0 for -inf scores); everywhere else a fixed share
+      // is evaluated on the FMA pipes
+      if (need_mask) exp_block(std::false_type{}); else exp_block(std::true_type{});
+      const float l0 = ls[0] + ls[2], l1 = ls[1] + ls[3];
       l += l0 + l1;
 #pragma unroll
       if (r == 0) FA2_STAMP(t, i, 4);

@@ -74,6 +74,55 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return d;
 }
 
+// 2^x for a pair of lanes evaluated on the FMA / ALU pipes instead of the MUFU (16 ex2 per clock per SM is the
+// co-bottleneck of attention on this chip). x is clamped to >= -125; valid up to x ~ +125. Cody-Waite split with the
+// round-to-nearest magic constant 1.5 * 2^23: t = x + magic holds n = round(x) in its low mantissa bits,
+// f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the 2^-9 of
+// the 16-bit rounding every probability goes through next), and n is added straight into the exponent field.
+__device__ __forceinline__ float2 ex2_emul2(float2 x) {
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = fadd2(x, magic);
+  const float2 n = fsub2(t, magic);
+  const float2 f = fsub2(x, n);
+  float2 p = ffma2(f, make_float2(0.05517167f, 0.05517167f), make_float2(0.24261113f, 0.24261113f));
+  p = ffma2(p, f, make_float2(0.69326097f, 0.69326097f));
+  p = ffma2(p, f, make_float2(0.99992806f, 0.99992806f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// scalar flavour (a lone warp on its scheduler issues FFMA / FADD every cycle, but an f32x2 op only every ~3)
+__device__ __forceinline__ float ex2_emul(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05517167f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// 2^(-t) with the same scheme, for callers that hold the negated exponent (t <= 125 after clamping)
+__device__ __forceinline__ float2 ex2_emul2_neg(float2 t) {
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  t.x = fminf(t.x, 125.f);
+  t.y = fminf(t.y, 125.f);
+  const float2 tm = fsub2(magic, t);  // magic + round(-t)
+  const float2 n = fsub2(tm, magic);  // round(-t)
+  const float2 g = fadd2(t, n);       // -(fraction) in [-0.5, 0.5]
+  float2 p = ffma2(g, make_float2(-0.05517167f, -0.05517167f), make_float2(0.24261113f, 0.24261113f));
+  p = ffma2(p, g, make_float2(-0.69326097f, -0.69326097f));
+  p = ffma2(p, g, make_float2(0.99992806f, 0.99992806f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(tm.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(tm.y) << 23));
+  return r;
+}
+
 // fire-and-forget fp32 vector reduction into global memory (REDG.E.ADD.F32x4); `p` must be 16-byte aligned
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
