@@ -266,57 +266,71 @@ def main():
     value = flops_global / (ms_step * 1e-3) / 1e12
 
     # -------------------------------- per-kernel timing (roofline of the dominant kernel) ------------------------
+    # Each kernel is launched alone through the C ABI with CUDA events on the launching stream on both sides.
     pk = peaks()
-    kern = {}
     n_rep = min(args.steps, 20)
     o, lse, scale, _ = fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
     stream = torch.cuda.current_stream().cuda_stream
     S_pad = math.ceil(S / 128) * 128
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    acc = {"fwd": 0.0, "delta": 0.0, "bwd": 0.0}
-    if bwd:
-        delta = torch.empty_like(lse)
-        dq = torch.empty_like(q)
-        dk, dv = torch.empty_like(k), torch.empty_like(v)
-        dq_mode = 0 if args.atomic else 1
-        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, dq_mode)
-        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
-        ws_ptr = ws.data_ptr() if ws_bytes else None
+    s3 = _lib.strides3
     o2, lse2 = torch.empty_like(o), torch.empty_like(lse)
-    for _ in range(n_rep):
-        marks = [ev() for _ in range(5)]
-        marks[0].record()
+    delta = torch.empty_like(lse)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, _lib.DQ_ATOMIC)
+    ws = torch.empty(ws_bytes if args.atomic else 16, device=dev, dtype=torch.uint8)
+
+    def call_fwd():
         _lib.check(lib.fa2_sm100_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o2.data_ptr(), lse2.data_ptr(),
-                                     B_local, H, H, S, S, D, _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
-                                     _lib.strides3(o2), S_pad, scale, int(causal), 17, stream), "fwd")
-        marks[1].record()
-        if bwd:
-            _lib.check(lib.fa2_sm100_bwd_delta(o.data_ptr(), do.data_ptr(), delta.data_ptr(), B_local, H, S, D,
-                                               _lib.strides3(o), _lib.strides3(do), S_pad, 17, ws_ptr, ws_bytes,
-                                               stream), "delta")
-            marks[2].record()
-            _lib.check(lib.fa2_sm100_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(),
-                                         delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws_ptr, ws_bytes,
-                                         B_local, H, H, S, S, D, _lib.strides3(do), _lib.strides3(q), _lib.strides3(k),
-                                         _lib.strides3(v), _lib.strides3(dq), _lib.strides3(dk), _lib.strides3(dv),
-                                         S_pad, scale, int(causal), dq_mode, 17, 17, stream), "bwd")
-            marks[3].record()
-            marks[4].record()
-        torch.cuda.synchronize()
-        acc["fwd"] += marks[0].elapsed_time(marks[1])
-        if bwd:
-            acc["delta"] += marks[1].elapsed_time(marks[2])
-            acc["bwd"] += marks[2].elapsed_time(marks[3])
-    kern = {k_: v_ / n_rep for k_, v_ in acc.items() if v_ > 0}
+                                     B_local, H, H, S, S, D, s3(q), s3(k), s3(v), s3(o2), S_pad, scale, int(causal), 17,
+                                     stream), "fwd")
+
+    def call_delta():
+        _lib.check(lib.fa2_sm100_bwd_delta(o.data_ptr(), do.data_ptr(), delta.data_ptr(), B_local, H, S, D, s3(o), s3(do),
+                                           S_pad, 17, ws.data_ptr() if args.atomic else None,
+                                           ws_bytes if args.atomic else 0, stream), "delta")
+
+    def call_bwd(mode):
+        need_ws = mode in (_lib.DQ_ATOMIC, _lib.DQ_FUSED_ORDERED)
+        _lib.check(lib.fa2_sm100_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(),
+                                     delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                     ws.data_ptr() if need_ws else None, ws_bytes if need_ws else 0,
+                                     B_local, H, H, S, S, D, s3(do), s3(q), s3(k), s3(v), s3(dq), s3(dk), s3(dv),
+                                     S_pad, scale, int(causal), mode, 17, 17, stream), "bwd")
+
+    def time_call(fn, pre=None):
+        tot = 0.0
+        for i in range(n_rep + 2):
+            if pre is not None:
+                pre()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                tot += a.elapsed_time(b)
+        return tot / n_rep
+
     f_fwd = fa_flops(B_local, H, S, S, D, causal, False)
+    kern = {"fa2_fwd_kernel": {"ms": time_call(call_fwd), "algorithmic_flop": f_fwd}}
     if bwd:
-        dom = "fa2_bwd_kernel + fa2_dq_convert_kernel" if args.atomic else "fa2_bwd_kernel (dK/dV) + fa2_bwd_dq_kernel"
-        dom_flops = 2.5 * f_fwd
-        dom_ms = kern["bwd"]
+        kern["fa2_delta_kernel"] = {"ms": time_call(call_delta), "algorithmic_flop": 0.0}
+        if args.atomic:
+            # the fused launch needs a cleared accumulator each time: the delta kernel does that, outside the events
+            kern["fa2_bwd_kernel<fused dQ> + fa2_dq_convert_kernel"] = {
+                "ms": time_call(lambda: call_bwd(_lib.DQ_ATOMIC), pre=call_delta), "algorithmic_flop": 2.5 * f_fwd}
+            dom = "fa2_bwd_kernel<fused dQ> + fa2_dq_convert_kernel"
+        else:
+            call_delta()
+            # S, dP, dV, dK are this kernel's own products; the dQ kernel recomputes S and dP (not counted) for dQ
+            kern["fa2_bwd_kernel<dK/dV>"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_NONE)), "algorithmic_flop": 2.0 * f_fwd}
+            kern["fa2_bwd_dq_kernel"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_ONLY)), "algorithmic_flop": 0.5 * f_fwd}
+            dom = "fa2_bwd_kernel<dK/dV>"
     else:
-        dom, dom_flops = "fa2_fwd_kernel", f_fwd
-        dom_ms = kern["fwd"]
-    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+        dom = "fa2_fwd_kernel"
+    for v_ in kern.values():
+        v_["tflops"] = v_["algorithmic_flop"] / (v_["ms"] * 1e-3) / 1e12 if v_["ms"] > 0 else 0.0
+    achieved = kern[dom]["tflops"]
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
@@ -325,9 +339,11 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["burst"], "unit": "TFLOP/s",
-                "frac": achieved / pk["burst"], "traffic": traffic, "peak_source": pk["source"] + " burst (kernel timed alone)",
+                "frac": achieved / pk["burst"], "traffic": traffic,
+                "peak_source": pk["source"] + " cuBLAS bf16 burst (kernel timed alone)",
                 "frac_of_sustained": achieved / pk["sustained"], "frac_of_nominal_2250": achieved / 2250.0,
-                "fwd_kernel_tflops": f_fwd / (kern["fwd"] * 1e-3) / 1e12, "kernel_ms": kern}
+                "algorithmic_flop_per_launch": kern[dom]["algorithmic_flop"], "kernel_ms": kern[dom]["ms"],
+                "kernels": kern}
 
     # ------------------------------------------------- e2e --------------------------------------------------------
     e2e = None

@@ -24,7 +24,8 @@ E_NULL_POINTER = -5
 E_WORKSPACE_TOO_SMALL = -6
 E_NO_DRIVER = -7
 
-DQ_ATOMIC, DQ_DETERMINISTIC, DQ_FUSED_ORDERED = 0, 1, 2  # the `deterministic` argument of fa2_sm100_bwd
+# the `deterministic` argument of fa2_sm100_bwd
+DQ_ATOMIC, DQ_DETERMINISTIC, DQ_FUSED_ORDERED, DQ_NONE, DQ_ONLY = 0, 1, 2, 3, 4
 
 DTYPE_FP16 = 16
 DTYPE_BF16 = 17

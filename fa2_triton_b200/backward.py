@@ -44,13 +44,17 @@ def _flash_attn_backward(
     dropout_seed: Optional[int],
     deterministic: Optional[bool] = None,
     dq_dtype: Optional[torch.dtype] = None,
-) -> Tuple[Tensor, Tensor, Tensor]:
+    need_dq: bool = True,
+    need_dkdv: bool = True,
+) -> Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor]]:
     """Returns ``(dq, dk, dv)`` like src/backward/caller.py:178: ``dq`` is fp32 ``[B, Sq, Hq, D]``
     (src/backward/caller.py:86), ``dk``/``dv`` are ``[B, Sk, Hkv, D]`` in the input dtype with the GQA
     head-group sum (src/backward/caller.py:163-165) already applied inside the kernel.
 
     ``dq_dtype`` (extension): write dq in that dtype instead of fp32. The autograd wrapper passes the input
-    dtype - the rounding autograd would apply to the reference's fp32 dq anyway - and saves one pass over dq."""
+    dtype - the rounding autograd would apply to the reference's fp32 dq anyway - and saves one pass over dq.
+    ``need_dq`` / ``need_dkdv`` (extension): skip the kernel whose outputs autograd does not ask for
+    (``ctx.needs_input_grad``); the skipped gradients are returned as ``None``."""
     _reject_out_of_scope(attention_mask, bias, dropout_p)
     dO = dO.contiguous() if dO.stride(-1) != 1 else dO
     batch_size, seqlen_q, nheads_q, head_dim = q.shape
@@ -67,15 +71,23 @@ def _flash_attn_backward(
     assert lse.dtype == torch.float32 and lse.is_contiguous()
     det = _DETERMINISTIC if deterministic is None else deterministic
     mode = int(det) if det in (0, 1, 2) else int(bool(det))  # True/False, or one of _lib.DQ_*
+    if not need_dq and not need_dkdv:
+        return None, None, None
+    if not need_dq:
+        mode = _lib.DQ_NONE
+    elif not need_dkdv:
+        mode = _lib.DQ_ONLY
 
     lib = _lib.load()
     dt = encode_dtype(q)
     with torch.cuda.device(q.device):
         stream = _stream_ptr(q.device)
         delta = torch.empty_like(lse)
-        dq = torch.empty_like(q, dtype=torch.float32 if dq_dtype is None else dq_dtype)
-        dk = torch.empty_like(k)
-        dv = torch.empty_like(v)
+        dq = torch.empty_like(q, dtype=torch.float32 if dq_dtype is None else dq_dtype) if need_dq else None
+        dk = torch.empty_like(k) if need_dkdv else None
+        dv = torch.empty_like(v) if need_dkdv else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        s3 = lambda t, like: _lib.strides3(t if t is not None else like)
         ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, mode)
         workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
         ws_ptr = workspace.data_ptr() if ws_bytes else None
@@ -87,10 +99,11 @@ def _flash_attn_backward(
         _lib.check(code, "fa2_sm100_bwd_delta")
         code = lib.fa2_sm100_bwd(
             dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws_ptr, ws_bytes,
+            ptr(dq), ptr(dk), ptr(dv), ws_ptr, ws_bytes,
             batch_size, nheads_q, nheads_kv, seqlen_q, seqlen_k, head_dim,
             _lib.strides3(dO), _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
-            _lib.strides3(dq), _lib.strides3(dk), _lib.strides3(dv),
-            max_seqlen_q_rounded, softmax_scale, int(bool(causal)), mode, dt, encode_dtype(dq), stream)
+            s3(dq, q), s3(dk, k), s3(dv, v),
+            max_seqlen_q_rounded, softmax_scale, int(bool(causal)), mode, dt,
+            encode_dtype(dq) if dq is not None else dt, stream)
         _lib.check(code, "fa2_sm100_bwd")
     return dq, dk, dv

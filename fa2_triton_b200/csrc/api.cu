@@ -155,7 +155,8 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic) {
   (void)Sk;
   if (B < 1 || Hq < 1 || Sq < 1 || D < 1) return 0;
-  if (deterministic == FA2_DQ_DETERMINISTIC) return 0;  // dQ is produced by its own kernel, no accumulator
+  if (deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_NONE || deterministic == FA2_DQ_ONLY)
+    return 0;  // dQ is produced by its own kernel (or not at all), no accumulator
   const size_t sq_pad = static_cast<size_t>(round_up(Sq, 128));
   const size_t accum = static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float);
   const size_t sem = static_cast<size_t>(B) * Hq * (sq_pad / 128) * sizeof(int);
@@ -169,15 +170,20 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
                   const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride, float softmax_scale,
                   int causal, int deterministic, int dtype, int dq_dtype, void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
-  if (!lse || !delta || !dq) return fail(FA2_E_NULL_POINTER, "lse / delta / dq: null pointer");
+  const bool want_dq = deterministic != FA2_DQ_NONE;
+  const bool want_dkdv = deterministic != FA2_DQ_ONLY;
+  if (!lse || !delta) return fail(FA2_E_NULL_POINTER, "lse / delta: null pointer");
+  if (want_dq && !dq) return fail(FA2_E_NULL_POINTER, "dq: null pointer");
   if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
   if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
-  if (deterministic < 0 || deterministic > 2) return fail(FA2_E_BAD_SHAPE, "deterministic must be 0, 1 or 2");
-  if (dq_dtype != dtype && dq_dtype != FA2_DTYPE_FP32)
-    return fail(FA2_E_UNSUPPORTED_DTYPE, "dq_dtype %d: must be the input dtype (%d) or 32 (fp32)", dq_dtype, dtype);
-  if (reinterpret_cast<uintptr_t>(dq) % 16) return fail(FA2_E_BAD_ALIGNMENT, "dq: base not 16-byte aligned");
-  for (int i = 0; i < 3; ++i)
-    if (dq_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "dq: strides must be multiples of 8 elements");
+  if (deterministic < 0 || deterministic > 4) return fail(FA2_E_BAD_SHAPE, "deterministic must be one of FA2_DQ_* (0..4)");
+  if (want_dq) {
+    if (dq_dtype != dtype && dq_dtype != FA2_DTYPE_FP32)
+      return fail(FA2_E_UNSUPPORTED_DTYPE, "dq_dtype %d: must be the input dtype (%d) or 32 (fp32)", dq_dtype, dtype);
+    if (reinterpret_cast<uintptr_t>(dq) % 16) return fail(FA2_E_BAD_ALIGNMENT, "dq: base not 16-byte aligned");
+    for (int i = 0; i < 3; ++i)
+      if (dq_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "dq: strides must be multiples of 8 elements");
+  }
   const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, Sk, D, deterministic);
   if (need > 0) {
     if (!workspace) return fail(FA2_E_NULL_POINTER, "workspace: null pointer");
@@ -190,12 +196,14 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   if (int e = make_tmap_bshd(&tk, k, dtype, B, Sk, Hkv, D, k_strides, 128, "k")) return e;
   if (int e = make_tmap_bshd(&tv, v, dtype, B, Sk, Hkv, D, v_strides, 128, "v")) return e;
   if (int e = make_tmap_bshd(&tdo, dout, dtype, B, Sq, Hq, D, do_strides, 128, "dout")) return e;
-  if (int e = make_tmap_bshd(&tdk, dk, dtype, B, Sk, Hkv, D, dk_strides, 128, "dk")) return e;
-  if (int e = make_tmap_bshd(&tdv, dv, dtype, B, Sk, Hkv, D, dv_strides, 128, "dv")) return e;
+  if (want_dkdv) {
+    if (int e = make_tmap_bshd(&tdk, dk, dtype, B, Sk, Hkv, D, dk_strides, 128, "dk")) return e;
+    if (int e = make_tmap_bshd(&tdv, dv, dtype, B, Sk, Hkv, D, dv_strides, 128, "dv")) return e;
+  }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int sq_pad = round_up(Sq, 128);
-  const bool fused = deterministic != FA2_DQ_DETERMINISTIC;
+  const bool fused = deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED;
   fa2::BwdParams p{};
   p.lse = lse; p.delta = delta;
   p.dq_accum = static_cast<float*>(workspace);
@@ -208,8 +216,12 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   p.scale_log2 = softmax_scale * kLog2e;
   p.causal = causal ? 1 : 0;
   p.deterministic = deterministic == FA2_DQ_FUSED_ORDERED ? 1 : 0;
-  cudaError_t ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
-  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
+  cudaError_t ce = cudaSuccess;
+  if (want_dkdv) {
+    ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
+  }
+  if (!want_dq) return 0;
 
   if (fused) {
     // dQ accumulator -> caller's tensor

@@ -8,12 +8,15 @@
 // Arithmetic: S = Q K^T, P = exp2(S c - LSE2), dP = dO V^T, dS = P o (dP - delta) rounded to
 // the input dtype, dQ = scale * (dS K) in fp32, stored in the caller's dtype.
 //
-// CTA = 12 warps:
-//   warps 0-3 / 4-7 : compute warpgroups; thread = query row (TMEM lane), warpgroup w owns key columns [64w, 64w+64)
-//   warp 8 : MMA issuer        warp 9 : TMA producer        warps 10-11 : idle
-// TMEM (512 columns): S ring [0,128) [128,256) | dP, then dS (16-bit, in place) [256,384) | dQ [384,384+D)
-// Tensor-pipe order:  S(0) dP(0) S(1) | dQ(i) dP(i+1) S(i+2) ...   - S is double buffered, so the exponentials of
-// block i+1 start as soon as dS(i) is handed over, and dP(i+1) is ready by the time they finish.
+// CTA = 20 warps:
+//   warps 0-15  : four compute warpgroups; thread = query row (TMEM lane), warpgroup g owns key columns [32g, 32g+32).
+//                 Four warps per scheduler instead of two: one warp of this code sustains ~0.3 instructions per clock
+//                 (dependent FFMA -> MUFU -> FMUL -> F2FP chains), so the block's softmax/dS latency - which sits on the
+//                 critical path between the tensor-pipe products - roughly halves (profiles/, ncu stall reasons).
+//   warp 16 : MMA issuer       warp 17 : TMA producer       warps 18-19 : idle
+// TMEM (512 columns): S ring [0,128) [128,256), dS(i) (16-bit) goes over S(i) | dP [256,384) | dQ [384,384+D)
+// Tensor-pipe order:  S(0) dP(0) S(1) | dP(i+1) dQ(i) S(i+2) ...   - S is double buffered, so the exponentials of
+// block i+1 start as soon as dS(i) is handed over, and dP(i+1) - the next thing they need - is issued first.
 #include "fa2_kernels.cuh"
 #include "ptx.cuh"
 
@@ -22,7 +25,9 @@ namespace fa2 {
 namespace {
 
 constexpr int kBlk = 128;
-constexpr int kDqThreads = 384;
+constexpr int kDqThreads = 640;
+constexpr int kCmpWgs = 4;             // compute warpgroups
+constexpr int kCmpCols = kBlk / kCmpWgs;  // key columns per compute thread
 constexpr int kKStages = 3;
 constexpr int kVStages = 2;
 
@@ -90,14 +95,14 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-  if (warp == 9 && lane == 0) {
+  if (warp == 17 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_do);
     if (p.dq_is_16bit) tma_prefetch_desc(&tmap_dq);
   }
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int s = 0; s < kKStages; ++s) {
@@ -111,7 +116,7 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       mbar_init(&s_full[0], 1);
       mbar_init(&s_full[1], 1);
       mbar_init(dp_full, 1);
-      mbar_init(ds_full, 256);
+      mbar_init(ds_full, kCmpWgs * 128);
       mbar_init(dq_done, 1);
       fence_barrier_init();
     }
@@ -123,9 +128,10 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   tcgen05_fence_after();
   if (*tmem_slot != 0u) __trap();  // whole-TMEM allocation => base 0 (keeps tcgen05 addresses warp-uniform)
 
-  if (warp >= 8) {
-    reg_dealloc<88>();
-  if (warp == 9) {
+  // register pool: 640 threads x 96 (launch bound) = 61440 >= 4 x 128 x 104 + 128 x 64
+  if (warp >= 16) {
+    reg_dealloc<64>();
+  if (warp == 17) {
     // ========================================= TMA producer ========================================
     if (nblk > 0 && elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * L::kTileBytes);
@@ -148,7 +154,7 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (++vs == kVStages) { vs = 0; vph ^= 1; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // ========================================== MMA issuer =========================================
     if (nblk > 0 && elect_one()) {
       constexpr uint32_t idesc_kk = make_idesc_f16(kBlk, kBlk, kBf16, false, false);  // S, dP: [q x D] [kv x D]^T
@@ -188,17 +194,9 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
       for (int i = 0; i < nblk; ++i) {
         const int ks = k_stage(i);
-        // dQ += dS(i) K(i)   (A = dS from TMEM: k-steps 0-3 in columns [0,32), 4-7 in [64,96) of the dP region)
-        mbar_wait(ds_full, i & 1);
+        mbar_wait(ds_full, i & 1);  // dS(i) is in tensor memory, and dP(i) / S(i) have been read
         tcgen05_fence_after();
-#pragma unroll
-        for (int k = 0; k < kBlk / 16; ++k) {
-          const uint32_t a_col = (k < 4) ? k * 8 : 64 + (k - 4) * 8;
-          umma_ts(kTmemDQ, kTmemDP + a_col, advance(k_mn, ks * L::kTileBytes + k * 2048), idesc_dq,
-                  (i > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&k_empty[ks]);  // K(i) has fed S(i) and dQ(i)
-        // dP(i+1) = dO V(i+1)^T  (overwrites dS(i): ordered after dQ(i) by the tensor pipe)
+        // dP(i+1) = dO V(i+1)^T first: it is what the compute warps wait for next
         if (i + 1 < nblk) {
           const int vs = (i + 1) % kVStages;
           mbar_wait(&v_full[vs], static_cast<uint32_t>(((i + 1) / kVStages) & 1));
@@ -207,7 +205,16 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           umma_commit(dp_full);
           umma_commit(&v_empty[vs]);
         }
-        // S(i+2) = Q K(i+2)^T into the buffer block i has just been read from
+        // dQ += dS(i) K(i)   (A = dS from TMEM: compute warpgroup g packed its 32 columns, k-steps 2g and 2g+1, into
+        // the first 16 columns of its slice of the S buffer block i was computed in)
+#pragma unroll
+        for (int k = 0; k < kBlk / 16; ++k) {
+          const uint32_t a_col = (k / 2) * kCmpCols + (k % 2) * 8;
+          umma_ts(kTmemDQ, kTmemS + (i & 1) * 128 + a_col, advance(k_mn, ks * L::kTileBytes + k * 2048), idesc_dq,
+                  (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&k_empty[ks]);  // K(i) has fed S(i) and dQ(i)
+        // S(i+2) = Q K(i+2)^T into the same buffer (ordered after dQ(i) by the tensor pipe)
         if (i + 2 < nblk) {
           const int ks2 = k_stage(i + 2);
           mbar_wait(&k_full[ks2], k_phase(i + 2));
@@ -221,66 +228,57 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
   } else {
     // ====================================== compute warpgroups =====================================
-    reg_alloc<208>();
+    reg_alloc<104>();
     const int wg = warp >> 2;
     const int r = threadIdx.x & 127;  // query row inside the block == TMEM lane
     const int row = row0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tDP = lane_sel + kTmemDP + wg * 64;
+    const uint32_t tDP = lane_sel + kTmemDP + wg * kCmpCols;
     const float c = p.scale_log2;
     // padded rows carry LSE = delta = 0 (forward / delta kernels); their dQ rows are never stored
     const int64_t stat_off = (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + row;
-    const float lse_r = p.lse[stat_off];
-    const float delta_r = p.delta[stat_off];
-    const float2 c2 = make_float2(c, c);
-    const float2 nl2 = make_float2(-lse_r, -lse_r);  // -inf -> +inf for fully masked rows: handled by the mask path
-    const float2 nd2 = make_float2(-delta_r, -delta_r);
+    const float nlse = -p.lse[stat_off];  // -inf -> +inf for fully masked rows: handled by the mask path
+    const float ndelta = -p.delta[stat_off];
 
     for (int i = 0; i < nblk; ++i) {
-      const uint32_t tS = lane_sel + kTmemS + (i & 1) * 128 + wg * 64;
-      const int col0 = i * kBlk + wg * 64;
+      const uint32_t tS = lane_sel + kTmemS + (i & 1) * 128 + wg * kCmpCols;
+      const int col0 = i * kBlk + wg * kCmpCols;
       const bool need_mask = (i * kBlk + kBlk > p.Sk) || (p.causal && (i * kBlk + kBlk - 1 > row0 + shift));
 
       // ---- P = exp2(S c - LSE) ----
       mbar_wait(&s_full[i & 1], (i >> 1) & 1);
       tcgen05_fence_after();
-      uint32_t su[2][32];
-      tmem_ld_32x32b_x32(tS, su[0]);
-      tmem_ld_32x32b_x32(tS + 32, su[1]);
+      uint32_t su[32];
+      tmem_ld_32x32b_x32(tS, su);
       tmem_wait_ld();
-      float2 pf[32];
+      float pf[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float2 t = ffma2(make_float2(__uint_as_float(su[j / 16][(2 * j) % 32]), __uint_as_float(su[j / 16][(2 * j) % 32 + 1])),
-                               c2, nl2);
-        // alternate pairs between the MUFU and the FMA pipes (ex2_emul2): halves the MUFU time of this phase
-        pf[j] = (j & 1) ? ex2_emul2(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        const float t = fmaf(__uint_as_float(su[j]), c, nlse);
+        // every fourth exponential on the FMA pipes, the others on the MUFU
+        pf[j] = ((j & 3) == 3) ? ex2_emul(t) : ex2_approx(t);
       }
       if (need_mask) {
         const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          pf[j].x = (col0 + 2 * j <= limit) ? pf[j].x : 0.f;
-          pf[j].y = (col0 + 2 * j + 1 <= limit) ? pf[j].y : 0.f;
-        }
+        for (int j = 0; j < 32; ++j) pf[j] = (col0 + j <= limit) ? pf[j] : 0.f;
       }
 
-      // ---- dS = P o (dP - delta), 16-bit, written in place over this warpgroup's dP columns ----
+      // ---- dS = P o (dP - delta), 16-bit, written over the head of this warpgroup's (now dead) S columns, so that
+      //      the dP columns are free for dP(i+1) at once ----
       mbar_wait(dp_full, i & 1);
       tcgen05_fence_after();
-      uint32_t dpu[2][32];
-      tmem_ld_32x32b_x32(tDP, dpu[0]);
-      tmem_ld_32x32b_x32(tDP + 32, dpu[1]);
+      uint32_t dpu[32];
+      tmem_ld_32x32b_x32(tDP, dpu);
       tmem_wait_ld();
-      uint32_t pk[32];
+      uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float2 x = fadd2(make_float2(__uint_as_float(dpu[j / 16][(2 * j) % 32]), __uint_as_float(dpu[j / 16][(2 * j) % 32 + 1])),
-                               nd2);
-        const float2 ds = fmul2(pf[j], x);
-        pk[j] = pack2<kBf16>(ds.x, ds.y);
+      for (int j = 0; j < 16; ++j) {
+        const float d0 = pf[2 * j] * (__uint_as_float(dpu[2 * j]) + ndelta);
+        const float d1 = pf[2 * j + 1] * (__uint_as_float(dpu[2 * j + 1]) + ndelta);
+        pk[j] = pack2<kBf16>(d0, d1);
       }
-      tmem_st_32x32b_x32(tDP, pk);
+      tmem_st_32x32b_x16(tS, pk);
       tmem_wait_st();
       tcgen05_fence_before();
       mbar_arrive(ds_full);
@@ -292,11 +290,11 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         mbar_wait(dq_done, 0);
         tcgen05_fence_after();
       }
-      constexpr int kColsPerWg = D / 2;
-      const uint32_t tDQ = lane_sel + kTmemDQ + wg * kColsPerWg;
+      // 32 head-dim columns per warpgroup: D / 32 of the four warpgroups take part
+      const uint32_t tDQ = lane_sel + kTmemDQ + wg * 32;
       const float mul = p.softmax_scale;
-#pragma unroll
-      for (int cidx = 0; cidx < kColsPerWg / 32; ++cidx) {
+      if (wg < D / 32) {
+        constexpr int cidx = 0;
         uint32_t o[32];
         if (nblk > 0) {
           tmem_ld_32x32b_x32(tDQ + cidx * 32, o);
@@ -305,7 +303,7 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = 0u;
         }
-        const int col = wg * kColsPerWg + cidx * 32;  // first head-dim column of this chunk
+        const int col = wg * 32;  // first head-dim column of this chunk
         if (p.dq_is_16bit) {
           uint8_t* sub = sQ + (col / 64) * kSubBytes;  // the Q tile is dead once dq_done fired
 #pragma unroll
@@ -329,11 +327,10 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       }
       if (p.dq_is_16bit) {
-        if (nblk == 0) {
-          // nothing was loaded into the Q tile, but q_full is only armed when nblk > 0: no load can race the zeros
-        }
+        // (when nblk == 0 nothing was loaded into the Q tile - q_full is only armed for nblk > 0 - so no load can
+        // race the zeros staged above)
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kCmpWgs * 128);
         if (threadIdx.x == 0) {
           for (int j = 0; j < kSub; ++j) tma_store_4d(&tmap_dq, sQ + j * kSubBytes, j * 64, row0, head, batch);
           bulk_commit_group();
@@ -345,7 +342,7 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tcgen05_fence_after();
     tmem_dealloc<512>(0u);
   }

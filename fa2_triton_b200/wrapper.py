@@ -66,6 +66,8 @@ class FlashAttnFunc(torch.autograd.Function):
             softmax_scale=ctx.softmax_scale,
             dropout_seed=ctx.dropout_seed,
             dq_dtype=q.dtype,
+            need_dq=ctx.needs_input_grad[0],
+            need_dkdv=ctx.needs_input_grad[1] or ctx.needs_input_grad[2],
         )
         return dq, dk, dv, None, None, None, None, None, None
 

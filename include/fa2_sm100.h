@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 3
+#define FA2_SM100_ABI_VERSION 4
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -49,6 +49,8 @@ extern "C" {
 #define FA2_DQ_ATOMIC 0         /* fused kernel, fp32 adds into an accumulator in arrival order (fast mode) */
 #define FA2_DQ_DETERMINISTIC 1  /* separate dQ kernel, one CTA per query block, fixed key-block order, no atomics */
 #define FA2_DQ_FUSED_ORDERED 2  /* fused kernel, adds serialised per query tile by a ticket (bit-repeatable, slowest) */
+#define FA2_DQ_NONE 3           /* dK and dV only (q does not require a gradient); dq may be NULL */
+#define FA2_DQ_ONLY 4           /* dQ only, deterministic kernel (k, v do not require gradients); dk, dv may be NULL */
 
 #define FA2_E_UNSUPPORTED_HEAD_DIM (-1)
 #define FA2_E_UNSUPPORTED_DTYPE (-2)

@@ -138,3 +138,18 @@ def test_delta_kernel():
     ref = (o.float() * do.float()).sum(-1).permute(0, 2, 1)
     torch.testing.assert_close(delta[:, :, :S], ref, rtol=1e-4, atol=1e-3)
     assert (delta[:, :, S:] == 0).all()
+
+
+def test_backward_skips_unneeded_gradients():
+    """Only q, or only k and v, require a gradient (ctx.needs_input_grad): the other kernel is not launched and the
+    gradients that are produced equal those of the full backward."""
+    q, k, v, do = generate_test_data(2, 384, 384, 4, 4, 128, torch.bfloat16, DEV, 12)
+    _, dq_all, dk_all, dv_all = ours_fwd_bwd(q, k, v, do, True)
+    qq = q.clone().requires_grad_(True)
+    out = fa2.flash_attn_func(qq, k, v, causal=True)
+    (dq_only,) = torch.autograd.grad(out, (qq,), do)
+    assert torch.equal(dq_only, dq_all)
+    kk, vv = k.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    out = fa2.flash_attn_func(q, kk, vv, causal=True)
+    dk_only, dv_only = torch.autograd.grad(out, (kk, vv), do)
+    assert torch.equal(dk_only, dk_all) and torch.equal(dv_only, dv_all)
