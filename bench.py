@@ -277,7 +277,7 @@ def main():
     delta = torch.empty_like(lse)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, _lib.DQ_ATOMIC)
-    ws = torch.empty(ws_bytes if args.atomic else 16, device=dev, dtype=torch.uint8)
+    ws = torch.empty(ws_bytes if args.atomic else 256, device=dev, dtype=torch.uint8)
 
     def call_fwd():
         _lib.check(lib.fa2_sm100_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o2.data_ptr(), lse2.data_ptr(),
@@ -290,10 +290,9 @@ def main():
                                            ws_bytes if args.atomic else 0, stream), "delta")
 
     def call_bwd(mode):
-        need_ws = mode in (_lib.DQ_ATOMIC, _lib.DQ_FUSED_ORDERED)
         _lib.check(lib.fa2_sm100_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(),
                                      delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                     ws.data_ptr() if need_ws else None, ws_bytes if need_ws else 0,
+                                     ws.data_ptr(), ws.numel(),
                                      B_local, H, H, S, S, D, s3(do), s3(q), s3(k), s3(v), s3(dq), s3(dk), s3(dv),
                                      S_pad, scale, int(causal), mode, 17, 17, stream), "bwd")
 

@@ -88,6 +88,7 @@ def _flash_attn_backward(
         dv = torch.empty_like(v) if need_dkdv else None
         ptr = lambda t: t.data_ptr() if t is not None else None
         s3 = lambda t, like: _lib.strides3(t if t is not None else like)
+        fused = mode in (_lib.DQ_ATOMIC, _lib.DQ_FUSED_ORDERED)
         ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, mode)
         workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
         ws_ptr = workspace.data_ptr() if ws_bytes else None
@@ -95,7 +96,8 @@ def _flash_attn_backward(
         # delta = rowsum(O * dO); the same launch clears the dQ accumulator when there is one
         code = lib.fa2_sm100_bwd_delta(
             o.data_ptr(), dO.data_ptr(), delta.data_ptr(), batch_size, nheads_q, seqlen_q, head_dim,
-            _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt, ws_ptr, ws_bytes, stream)
+            _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt,
+            ws_ptr if fused else None, ws_bytes if fused else 0, stream)
         _lib.check(code, "fa2_sm100_bwd_delta")
         code = lib.fa2_sm100_bwd(
             dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(), delta.data_ptr(),

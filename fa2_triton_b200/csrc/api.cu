@@ -155,8 +155,9 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic) {
   (void)Sk;
   if (B < 1 || Hq < 1 || Sq < 1 || D < 1) return 0;
-  if (deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_NONE || deterministic == FA2_DQ_ONLY)
-    return 0;  // dQ is produced by its own kernel (or not at all), no accumulator
+  if (deterministic == FA2_DQ_NONE) return 0;
+  if (deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_ONLY)
+    return 256;  // dQ is produced by its own kernel: no accumulator, only the work-item counter of its scheduler
   const size_t sq_pad = static_cast<size_t>(round_up(Sq, 128));
   const size_t accum = static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float);
   const size_t sem = static_cast<size_t>(B) * Hq * (sq_pad / 128) * sizeof(int);
@@ -230,8 +231,12 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   CUtensorMap tdq = tq;  // placeholder when dq is fp32 (the kernel then stores through plain pointers)
   if (dq_dtype == dtype)
     if (int e = make_tmap_bshd(&tdq, dq, dtype, B, Sq, Hq, D, dq_strides, 128, "dq")) return e;
+  // work-item counter of the persistent dQ kernel (it re-zeroes it itself; this covers the first use of the buffer)
+  ce = cudaMemsetAsync(workspace, 0, 16, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd scheduler counter memset");
   fa2::DqParams d{};
   d.lse = lse; d.delta = delta; d.dq = dq;
+  d.sched = static_cast<int*>(workspace);
   for (int i = 0; i < 3; ++i) d.dq_strides[i] = dq_strides[i];
   d.dq_is_16bit = dq_dtype == dtype ? 1 : 0;
   d.B = B; d.Hq = Hq; d.Hkv = Hkv; d.Sq = Sq; d.Sk = Sk;
@@ -269,7 +274,7 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
 
 #ifdef FA2_TRACE
 int fa2_sm100_debug_fetch_trace(int which, long long* host, size_t n) {
-  return static_cast<int>(which == 0 ? fa2::fetch_fwd_trace(host, n) : fa2::fetch_bwd_trace(host, n));
+  return static_cast<int>(which == 0 ? fa2::fetch_fwd_trace(host, n) : (which == 1 ? fa2::fetch_bwd_trace(host, n) : fa2::fetch_dq_trace(host, n)));
 }
 #endif
 

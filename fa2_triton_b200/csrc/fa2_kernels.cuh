@@ -61,7 +61,8 @@ cudaError_t launch_bwd(int D, bool bf16, bool fused_dq, const CUtensorMap& tq, c
 struct DqParams {
   const float* lse;    // [B, Hq, lse_stride] log2 domain
   const float* delta;  // [B, Hq, lse_stride]
-  void* dq;            // [B, Sq, Hq, D] (used directly when dq_is_16bit == 0, otherwise through the tensor map)
+  int* sched;          // work-item counter of the persistent scheduler: one int, 0 on entry (the kernel re-zeroes it)
+  void* dq;            // [B, Sq, Hq, D]
   int64_t dq_strides[3];  // batch, head, seq (elements)
   int dq_is_16bit;     // 1: dq has the input dtype (TMA store), 0: dq is fp32 (vector stores)
   int B, Hq, Hkv, Sq, Sk;
@@ -104,6 +105,7 @@ cudaError_t launch_probe(bool bf16, const CUtensorMap& ta, const CUtensorMap& tb
 #ifdef FA2_TRACE
 cudaError_t fetch_fwd_trace(long long* host, size_t n);
 cudaError_t fetch_bwd_trace(long long* host, size_t n);
+cudaError_t fetch_dq_trace(long long* host, size_t n);
 #endif
 
 }  // namespace fa2

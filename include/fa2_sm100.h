@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 4
+#define FA2_SM100_ABI_VERSION 5
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -78,15 +78,16 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
                         const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride,
                         int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Bytes of scratch fa2_sm100_bwd needs: 0 in FA2_DQ_DETERMINISTIC mode; otherwise the fp32 dQ accumulator plus one
- * int per (batch, head, 128-row query tile). The workspace must be 16-byte aligned. */
+/* Bytes of scratch fa2_sm100_bwd needs. FA2_DQ_ATOMIC / FA2_DQ_FUSED_ORDERED: the fp32 dQ accumulator plus one int per
+ * (batch, head, 128-row query tile). FA2_DQ_DETERMINISTIC / FA2_DQ_ONLY: 256 bytes (work-item counter of the
+ * persistent dQ kernel; cleared by the call itself). FA2_DQ_NONE: 0. The workspace must be 16-byte aligned. */
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic);
 
 /* dQ ([B, Sq, Hq, D], `dq_dtype` = the input dtype or 32 for fp32 as the reference allocates it at
  * src/backward/caller.py:86), dK and dV (input dtype, [B, Sk, Hkv, D], GQA head groups already summed).
- * `deterministic` selects the dQ path (FA2_DQ_*). Modes 0 and 2 need `workspace`, all zero on entry: pass it to
- * fa2_sm100_bwd_delta (same stream) or clear it yourself. Mode 1 ignores `workspace`. Results of modes 1 and 2 are
- * bit-identical run to run. */
+ * `deterministic` selects the dQ path (FA2_DQ_*). Modes 0 and 2 need `workspace` all zero on entry: pass it to
+ * fa2_sm100_bwd_delta (same stream) or clear it yourself. Modes 1 and 4 clear their 256 bytes themselves; one call
+ * per workspace may be in flight at a time. Results of modes 1, 2 and 4 are bit-identical run to run. */
 int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
                   const float* lse, const float* delta,
                   void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes,

@@ -1,40 +1,42 @@
-// Microbenchmark: tcgen05.mma issue/throughput for SS vs TS operands and N = 128 / 256, alone and with concurrent
-// shared-memory traffic from other warps. Operand contents are garbage (uninitialised smem) - only timing matters.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../fa2_triton_b200/csrc -o umma_rate umma_rate.cu
+// Microbenchmark: tcgen05.mma throughput (cycles per instruction, one issuing thread per SM) for
+//   SS vs TS operands, N = 128 / 256, one or two accumulator tiles, K-major vs MN-major B,
+// optionally with concurrent shared-memory traffic from 8 other warps. Everything is a template parameter so that
+// the issue loop is as tight as in the real kernels (descriptor add + UTCHMMA). Operand contents are garbage.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../fa2_triton_b200/csrc -o umma_rate umma_rate.cu
 #include <cstdio>
 #include "ptx.cuh"
 using namespace fa2;
 
-// mode: 0 = SS N=128, 1 = TS N=128, 2 = SS N=256, 3 = TS N=256 ; traffic: 0 none, 1 LDS.128 stream, 2 STS.128 stream
-__global__ void __launch_bounds__(288, 1) k(long long* out, int iters, int mode, int traffic) {
+template <bool TS, int N, int NACC, bool BMN, bool SAME>
+__global__ void __launch_bounds__(288, 1) k(long long* out, int iters, int traffic) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
+  __shared__ volatile int done;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); done = 0; }
     __syncwarp();
     tmem_alloc<512>(&slot);
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  __shared__ volatile int done;
-  if (threadIdx.x == 0) done = 0;
-  __syncthreads();
   if (warp == 0) {
     if (elect_one()) {
-      const int N = (mode >= 2) ? 256 : 128;
-      const uint32_t idesc = make_idesc_f16(128, N, true, false, false);
+      constexpr uint32_t idesc = make_idesc_f16(128, N, true, false, BMN);
       const SmemDesc a = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
-      const SmemDesc b = make_smem_desc_sw128(smem_u32(smem) + 32768, 16, 1024);
+      const SmemDesc b = BMN ? make_smem_desc_sw128(smem_u32(smem) + 32768, 16384, 1024)
+                             : make_smem_desc_sw128(smem_u32(smem) + 32768, 16, 1024);
       long long t0 = clock64();
       for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          if (mode & 1) umma_ts(0, 256 + kk * 8, advance(b, off), idesc, 1u);
-          else umma_ss(0, advance(a, off), advance(b, off), idesc, 1u);
+          const uint32_t off = SAME ? 0u : (kk / 4) * 16384 + (kk % 4) * 32;
+          const uint32_t boff = SAME ? 0u : (BMN ? kk * 2048 : off);
+          const uint32_t d = (kk % NACC) * 128;
+          if (TS) umma_ts(d, 448 + kk * 8, advance(b, boff), idesc, 1u);
+          else umma_ss(d, advance(a, off), advance(b, boff), idesc, 1u);
         }
       }
       umma_commit(&bar);
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(288, 1) k(long long* out, int iters, int mode,
     }
   } else if (traffic) {
     uint4* p = reinterpret_cast<uint4*>(smem + 98304) + (threadIdx.x - 32);
-    uint4 acc = make_uint4(0, 0, 0, 0);
+    uint4 acc = make_uint4(threadIdx.x, 0, 0, 0);
     long long n = 0;
     while (!done) {
 #pragma unroll
@@ -63,22 +65,33 @@ __global__ void __launch_bounds__(288, 1) k(long long* out, int iters, int mode,
   if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<512>(0u); }
 }
 
+template <bool TS, int N, int NACC, bool BMN, bool SAME>
+void run(const char* name, long long* d) {
+  auto kern = k<TS, N, NACC, BMN, SAME>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 2000;
+  for (int tr = 0; tr < 3; ++tr) {
+    cudaMemset(d, 0, 64);
+    kern<<<148, 288, 200 * 1024>>>(d, iters, tr);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[3]; cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
+    printf("%-44s %-16s: %s  %6.1f cycles per MMA (math alone: %d)\n", name,
+           tr == 0 ? "alone" : (tr == 1 ? "+8 warps LDS.128" : "+8 warps STS.128"), cudaGetErrorString(e),
+           double(h[0]) / (iters * 8.0), N / 2);
+  }
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 64);
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int iters = 2000;
-  const char* mn[] = {"SS N=128", "TS N=128", "SS N=256", "TS N=256"};
-  const char* tn[] = {"no other smem traffic", "8 warps LDS.128", "8 warps STS.128"};
-  for (int mode = 0; mode < 4; ++mode)
-    for (int tr = 0; tr < 3; ++tr) {
-      cudaMemset(d, 0, 64);
-      k<<<148, 288, 200 * 1024>>>(d, iters, mode, tr);
-      cudaError_t e = cudaDeviceSynchronize();
-      long long h[3]; cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
-      const double per = double(h[0]) / (iters * 8.0);
-      const int N = mode >= 2 ? 256 : 128;
-      printf("%-9s %-24s: %s  %.1f cycles per MMA (ideal %d)  other-warp smem ops: %.1f B/clk\n", mn[mode], tn[tr], cudaGetErrorString(e), per,
-             N / 2, tr ? double(h[2]) * 8 * 32 * 16 / double(h[0]) : 0.0);
-    }
+  run<false, 128, 1, false, false>("SS N=128 K-major B, 1 accumulator", d);
+  run<false, 128, 2, false, false>("SS N=128 K-major B, 2 accumulators", d);
+  run<false, 128, 1, false, true>("SS N=128 K-major B, same operands", d);
+  run<false, 128, 1, true, false>("SS N=128 MN-major B, 1 accumulator", d);
+  run<true, 128, 1, false, false>("TS N=128 K-major B, 1 accumulator", d);
+  run<true, 128, 1, true, false>("TS N=128 MN-major B, 1 accumulator", d);
+  run<true, 128, 2, true, false>("TS N=128 MN-major B, 2 accumulators", d);
+  run<true, 128, 1, true, true>("TS N=128 MN-major B, same operands", d);
+  run<false, 256, 1, false, false>("SS N=256 K-major B, 1 accumulator", d);
+  run<true, 256, 1, false, false>("TS N=256 K-major B, 1 accumulator", d);
   return 0;
 }

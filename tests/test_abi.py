@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/fa2_sm100.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.fa2_sm100_version() == 4
+    assert lib.fa2_sm100_version() == 5
 
 
 def test_workspace_size_formula():
@@ -40,8 +40,10 @@ def test_workspace_size_formula():
     assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 0) == 4 * 32 * 4096 * 128 * 4 + 4 * 32 * 32 * 4
     assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 1000, 1000, 64, 2) == 1024 * 64 * 4 + 32
     assert lib.fa2_sm100_bwd_workspace_bytes(0, 1, 1, 1, 64, 0) == 0
-    # deterministic: dQ has its own kernel, nothing to accumulate into
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1) == 0
+    # deterministic / dQ only: dQ has its own kernel, nothing to accumulate into - just its scheduler's counter
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1) == 256
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 4) == 256
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 3) == 0
 
 
 def test_argument_errors_need_no_gpu():
