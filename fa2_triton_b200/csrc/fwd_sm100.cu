@@ -52,6 +52,12 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between
 #ifndef FA2_FWD_EMUL_DEN
 #define FA2_FWD_EMUL_DEN 4
 #endif
+// Speculative exponentials against the previous reference maximum (see the softmax loop). Off by default: measured
+// slower than the two-pass form on B200 (0.77 vs 0.57-0.64 ms) - the block's 128 scores and 64 packed results are
+// live together and the FMNMX no longer hide behind anything.
+#ifndef FA2_FWD_SPEC
+#define FA2_FWD_SPEC 0
+#endif
 
 template <int D>
 struct FwdSmem {
@@ -298,6 +304,36 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int j = 0; j < kBN; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
       }
 
+      uint32_t pk[kBN / 64][32];
+      // Speculative fast path (every block but the first and the masked ones): exponentiate against the current
+      // reference maximum right away and find the block maximum on the side - the FMNMX run on the ALU pipe in the
+      // shadow of the MUFU. Only if some row of this warp turns out to exceed the reference by more than the rescale
+      // threshold is the block redone the slow way (maximum first, rescale O, exponentiate). Results are identical
+      // to always taking the slow path; the ~500-cycle maximum pass leaves the softmax -> PV -> QK chain.
+      bool done = false;
+      if (FA2_FWD_SPEC && i > 0 && !need_mask) {
+        const float neg_m = -m_ref;  // m_ref == -inf (row without any visible key so far) forces the slow path below
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        float xm[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xm[e] = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kBN; j += 2) {
+          const float x0 = fmaf(s[j], c, neg_m), x1 = fmaf(s[j + 1], c, neg_m);
+          xm[(j / 2) % 8] = fmaxf(xm[(j / 2) % 8], fmaxf(x0, x1));
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          ls[j % 4] += p0;
+          ls[j % 4 + 1] += p1;
+          pk[j / 64][(j / 2) % 32] = pack2<kBf16>(p0, p1);
+        }
+        const float xmax = fmaxf(fmaxf(fmaxf(xm[0], xm[1]), fmaxf(xm[2], xm[3])), fmaxf(fmaxf(xm[4], xm[5]), fmaxf(xm[6], xm[7])));
+        const bool redo = !(xmax <= kRescaleThreshold);  // also true for NaN (m_ref == -inf)
+        if (!__any_sync(0xffffffffu, redo)) {
+          l += (ls[0] + ls[2]) + (ls[1] + ls[3]);
+          done = true;
+        }
+      }
+      if (!done) {
       float mx[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[j], s[j + 8]);
@@ -331,7 +367,6 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (r == 0) FA2_STAMP(t, i, 3);
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[kBN / 64][32];
       auto exp_block = [&](auto emulate) {
 #pragma unroll
         for (int j = 0; j < kBN; j += 2) {
@@ -354,8 +389,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (need_mask) exp_block(std::false_type{}); else exp_block(std::true_type{});
       const float l0 = ls[0] + ls[2], l1 = ls[1] + ls[3];
       l += l0 + l1;
-#pragma unroll
+      }
       if (r == 0) FA2_STAMP(t, i, 4);
+#pragma unroll
       for (int cidx = 0; cidx < kBN / 64; ++cidx) tmem_st_32x32b_x32(tS + cidx * 32, pk[cidx]);
       tmem_wait_st();
       tcgen05_fence_before();
