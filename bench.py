@@ -276,8 +276,9 @@ def main():
     o2, lse2 = torch.empty_like(o), torch.empty_like(lse)
     delta = torch.empty_like(lse)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, _lib.DQ_ATOMIC)
-    ws = torch.empty(ws_bytes if args.atomic else 256, device=dev, dtype=torch.uint8)
+    ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(B_local, H, S, S, D, int(causal),
+                                                 _lib.DQ_ATOMIC if args.atomic else _lib.DQ_DET_SPILL)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
 
     def call_fwd():
         _lib.check(lib.fa2_sm100_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o2.data_ptr(), lse2.data_ptr(),
@@ -321,14 +322,18 @@ def main():
             dom = "fa2_bwd_kernel<fused dQ> + fa2_dq_convert_kernel"
         else:
             call_delta()
-            # S, dP, dV, dK are this kernel's own products; the dQ kernel recomputes S and dP (not counted) for dQ
-            kern["fa2_bwd_kernel<dK/dV>"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_NONE)), "algorithmic_flop": 2.0 * f_fwd}
-            kern["fa2_bwd_dq_kernel"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_ONLY)), "algorithmic_flop": 0.5 * f_fwd}
-            dom = "fa2_bwd_kernel<dK/dV>"
+            # S, dP, dV, dK are the dK/dV kernel's products (it also spills dS); the dQ kernel's one product is dS K
+            kern["fa2_bwd_dkdv_kernel<spill>"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_SPILL_DKDV)), "algorithmic_flop": 2.0 * f_fwd}
+            kern["fa2_bwd_dq_spill_kernel"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_SPILL_DQ)), "algorithmic_flop": 0.5 * f_fwd,
+                                               "bound": "hbm", "algorithmic_bytes": float(ws_bytes - 1024 + 2 * q.numel() * 2)}
+            dom = "fa2_bwd_dkdv_kernel<spill>"
     else:
         dom = "fa2_fwd_kernel"
     for v_ in kern.values():
         v_["tflops"] = v_["algorithmic_flop"] / (v_["ms"] * 1e-3) / 1e12 if v_["ms"] > 0 else 0.0
+        if "algorithmic_bytes" in v_:  # HBM-bound kernels: bytes each launch has to move / its duration
+            v_["gbs"] = v_["algorithmic_bytes"] / (v_["ms"] * 1e-3) / 1e9
+            v_["frac_of_hbm_peak"] = v_["gbs"] / pk["hbm"]
     achieved = kern[dom]["tflops"]
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
@@ -380,7 +385,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, w), "per_gpu_batch": B_local, "global_batch": B_global,
                        "sharding": f"batch x head units over {world} GPU(s), no data-path collective",
-                       "dq_mode": "atomic" if args.atomic else "deterministic",
+                       "dq_mode": "atomic" if args.atomic else "deterministic (dS tiles spilled by the dK/dV kernel, dQ = sum dS K in fixed order)",
                        "l2": "inputs (q,k,v,o,dO = 5 x 128 MiB at cfg3) exceed the 126 MB L2; no explicit flush",
                        "api": "fa2_triton_b200.flash_attn_func + torch.autograd.grad"},
             "frac_of_measured_burst_peak": value / world / pk["burst"],

@@ -25,7 +25,7 @@ E_WORKSPACE_TOO_SMALL = -6
 E_NO_DRIVER = -7
 
 # the `deterministic` argument of fa2_sm100_bwd
-DQ_ATOMIC, DQ_DETERMINISTIC, DQ_FUSED_ORDERED, DQ_NONE, DQ_ONLY = 0, 1, 2, 3, 4
+DQ_ATOMIC, DQ_DETERMINISTIC, DQ_FUSED_ORDERED, DQ_NONE, DQ_ONLY, DQ_DET_SPILL, DQ_SPILL_DKDV, DQ_SPILL_DQ = range(8)
 
 DTYPE_FP16 = 16
 DTYPE_BF16 = 17
@@ -43,7 +43,7 @@ SIGNATURES = {
                       + [_c_int64, _c_float, _c_int, _c_int, _c_void_p]),
     "fa2_sm100_bwd_delta": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)] * 2
                             + [_c_int64, _c_int, _c_void_p, _c_size_t, _c_void_p]),
-    "fa2_sm100_bwd_workspace_bytes": (_c_size_t, [_c_int] * 6),
+    "fa2_sm100_bwd_workspace_bytes": (_c_size_t, [_c_int] * 7),
     "fa2_sm100_bwd": (_c_int, [_c_void_p] * 10 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 7
                       + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "fa2_sm100_dq_convert": (_c_int, [_c_void_p] * 2 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)]

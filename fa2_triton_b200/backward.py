@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -12,17 +13,26 @@ from . import _lib
 from .forward import _reject_out_of_scope, _stream_ptr, encode_dtype
 
 # Process-wide default for how dQ contributions are summed.
-#   True / 1 : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
-#              fixed order, no atomics (what the reference's kernel does, src/backward/kernel.py:154-182).
+#   True     : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
+#              fixed order, no atomics (what the reference's kernel does, src/backward/kernel.py:154-182). The dK/dV
+#              kernel spills its 16-bit dS tiles to a workspace (32 KB per visible 128 x 128 block pair) and the dQ
+#              kernel only sums dS K over them: 5 matrix products per block pair (mode 5). If that workspace does
+#              not fit (FA2_SPILL_MAX_GIB, default 72, or an allocation failure) the dQ kernel recomputes S, P, dP and
+#              dS like the reference (7 products, 256 bytes of workspace; mode 1).
+#   1 / 5    : force the recomputing / the spilling deterministic path.
 #   False / 0: atomic fast mode - the dK/dV kernel also forms dQ partial products and adds them into an fp32
-#              accumulator in arrival order (5 instead of 7 matrix products per block pair).
+#              accumulator in arrival order (5 products per block pair).
 #   2        : the fused kernel with the adds serialised per query tile by a ticket (bit-repeatable as well).
 _DETERMINISTIC = True
 
 
 def set_deterministic(flag) -> None:
     global _DETERMINISTIC
-    _DETERMINISTIC = flag if flag in (0, 1, 2) and not isinstance(flag, bool) else bool(flag)
+    _DETERMINISTIC = flag if flag in (0, 1, 2, 5) and not isinstance(flag, bool) else bool(flag)
+
+
+def _spill_limit_bytes() -> int:
+    return int(float(os.environ.get("FA2_SPILL_MAX_GIB", "72")) * (1 << 30))
 
 
 def is_deterministic() -> bool:
@@ -70,7 +80,11 @@ def _flash_attn_backward(
     assert q.dtype == k.dtype == v.dtype == o.dtype == dO.dtype, "All tensors must have the same type"
     assert lse.dtype == torch.float32 and lse.is_contiguous()
     det = _DETERMINISTIC if deterministic is None else deterministic
-    mode = int(det) if det in (0, 1, 2) else int(bool(det))  # True/False, or one of _lib.DQ_*
+    auto = isinstance(det, bool) and det  # True: spill when the workspace fits, else recompute
+    if isinstance(det, bool):
+        mode = _lib.DQ_DET_SPILL if det else _lib.DQ_ATOMIC
+    else:
+        mode = int(det) if det in (0, 1, 2, 5) else int(bool(det))  # one of _lib.DQ_*
     if not need_dq and not need_dkdv:
         return None, None, None
     if not need_dq:
@@ -89,8 +103,20 @@ def _flash_attn_backward(
         ptr = lambda t: t.data_ptr() if t is not None else None
         s3 = lambda t, like: _lib.strides3(t if t is not None else like)
         fused = mode in (_lib.DQ_ATOMIC, _lib.DQ_FUSED_ORDERED)
-        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, mode)
-        workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
+        ws_args = (batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, int(bool(causal)))
+        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(*ws_args, mode)
+        workspace = None
+        if auto and mode == _lib.DQ_DET_SPILL:
+            if ws_bytes <= _spill_limit_bytes():
+                try:
+                    workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+                except torch.OutOfMemoryError:
+                    workspace = None
+            if workspace is None:  # no room for the dS tiles: the recomputing dQ kernel needs 256 bytes
+                mode = _lib.DQ_DETERMINISTIC
+                ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(*ws_args, mode)
+        if workspace is None and ws_bytes:
+            workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
         ws_ptr = workspace.data_ptr() if ws_bytes else None
 
         # delta = rowsum(O * dO); the same launch clears the dQ accumulator when there is one

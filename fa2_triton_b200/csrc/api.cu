@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -136,7 +137,7 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, in
   p.lse_stride = static_cast<int>(lse_row_stride);
   for (int i = 0; i < 3; ++i) { p.o_strides[i] = o_strides[i]; p.do_strides[i] = do_strides[i]; }
   if (workspace) {
-    const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, 1, D, FA2_DQ_ATOMIC);
+    const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, 1, D, 0, FA2_DQ_ATOMIC);
     if (workspace_bytes < need)
       return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
     if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FA2_E_BAD_ALIGNMENT, "workspace not 16-byte aligned");
@@ -152,12 +153,17 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, in
 int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq, int D, const int64_t dq_strides[3],
                          float softmax_scale, int out_dtype, void* stream);
 
-size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic) {
-  (void)Sk;
+size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int causal, int deterministic) {
   if (B < 1 || Hq < 1 || Sq < 1 || D < 1) return 0;
   if (deterministic == FA2_DQ_NONE) return 0;
   if (deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_ONLY)
     return 256;  // dQ is produced by its own kernel: no accumulator, only the work-item counter of its scheduler
+  if (deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ) {
+    // scheduler counter (padded to 1 KB) + one 32 KB dS tile per visible (query block, key block) pair
+    if (Sk < 1) return 0;
+    const long long tiles = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);
+    return 1024 + static_cast<size_t>(B) * Hq * static_cast<size_t>(tiles) * fa2::kDsTileBytes;
+  }
   const size_t sq_pad = static_cast<size_t>(round_up(Sq, 128));
   const size_t accum = static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float);
   const size_t sem = static_cast<size_t>(B) * Hq * (sq_pad / 128) * sizeof(int);
@@ -171,13 +177,13 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
                   const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride, float softmax_scale,
                   int causal, int deterministic, int dtype, int dq_dtype, void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
-  const bool want_dq = deterministic != FA2_DQ_NONE;
-  const bool want_dkdv = deterministic != FA2_DQ_ONLY;
+  const bool want_dq = deterministic != FA2_DQ_NONE && deterministic != FA2_DQ_SPILL_DKDV;
+  const bool want_dkdv = deterministic != FA2_DQ_ONLY && deterministic != FA2_DQ_SPILL_DQ;
   if (!lse || !delta) return fail(FA2_E_NULL_POINTER, "lse / delta: null pointer");
   if (want_dq && !dq) return fail(FA2_E_NULL_POINTER, "dq: null pointer");
   if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
   if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
-  if (deterministic < 0 || deterministic > 4) return fail(FA2_E_BAD_SHAPE, "deterministic must be one of FA2_DQ_* (0..4)");
+  if (deterministic < 0 || deterministic > 7) return fail(FA2_E_BAD_SHAPE, "deterministic must be one of FA2_DQ_* (0..7)");
   if (want_dq) {
     if (dq_dtype != dtype && dq_dtype != FA2_DTYPE_FP32)
       return fail(FA2_E_UNSUPPORTED_DTYPE, "dq_dtype %d: must be the input dtype (%d) or 32 (fp32)", dq_dtype, dtype);
@@ -185,7 +191,7 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
     for (int i = 0; i < 3; ++i)
       if (dq_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "dq: strides must be multiples of 8 elements");
   }
-  const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, Sk, D, deterministic);
+  const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, Sk, D, causal, deterministic);
   if (need > 0) {
     if (!workspace) return fail(FA2_E_NULL_POINTER, "workspace: null pointer");
     if (workspace_bytes < need)
@@ -218,8 +224,26 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   p.causal = causal ? 1 : 0;
   p.deterministic = deterministic == FA2_DQ_FUSED_ORDERED ? 1 : 0;
   cudaError_t ce = cudaSuccess;
+  const bool spill = deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ;
+  const long long tiles_per_head = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);
+  void* spill_base = spill ? static_cast<char*>(workspace) + 1024 : nullptr;
   if (want_dkdv) {
-    ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
+    // FA2_SM100_OLD_DKDV=1 (A/B switch): the unfused instantiation of the fused kernel, P^T kept in tensor memory
+    static const bool old_dkdv = [] { const char* e = getenv("FA2_SM100_OLD_DKDV"); return e && e[0] == '1'; }();
+    if (fused || (old_dkdv && !spill)) {
+      ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
+    } else {
+      fa2::DkdvParams k{};
+      k.lse = lse; k.delta = delta;
+      k.ds_spill = spill_base;
+      k.tiles_per_head = tiles_per_head;
+      k.B = B; k.Hq = Hq; k.Hkv = Hkv; k.Sq = Sq; k.Sk = Sk;
+      k.lse_stride = static_cast<int>(lse_row_stride);
+      k.softmax_scale = softmax_scale;
+      k.scale_log2 = softmax_scale * kLog2e;
+      k.causal = causal ? 1 : 0;
+      ce = fa2::launch_bwd_dkdv(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
+    }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
   }
   if (!want_dq) return 0;
@@ -228,12 +252,27 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
     // dQ accumulator -> caller's tensor
     return fa2_sm100_dq_convert(workspace, dq, B, Hq, Sq, D, dq_strides, softmax_scale, dq_dtype, stream);
   }
-  CUtensorMap tdq = tq;  // placeholder when dq is fp32 (the kernel then stores through plain pointers)
-  if (dq_dtype == dtype)
-    if (int e = make_tmap_bshd(&tdq, dq, dtype, B, Sq, Hq, D, dq_strides, 128, "dq")) return e;
   // work-item counter of the persistent dQ kernel (it re-zeroes it itself; this covers the first use of the buffer)
   ce = cudaMemsetAsync(workspace, 0, 16, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd scheduler counter memset");
+  if (spill) {
+    fa2::DqSpillParams d{};
+    d.ds_spill = spill_base;
+    d.tiles_per_head = tiles_per_head;
+    d.sched = static_cast<int*>(workspace);
+    d.dq = dq;
+    for (int i = 0; i < 3; ++i) d.dq_strides[i] = dq_strides[i];
+    d.dq_is_16bit = dq_dtype == dtype ? 1 : 0;
+    d.B = B; d.Hq = Hq; d.Hkv = Hkv; d.Sq = Sq; d.Sk = Sk;
+    d.softmax_scale = softmax_scale;
+    d.causal = causal ? 1 : 0;
+    ce = fa2::launch_bwd_dq_spill(D, dtype == FA2_DTYPE_BF16, tk, d, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ (spill) launch");
+    return 0;
+  }
+  CUtensorMap tdq = tq;  // placeholder when dq is fp32 (the kernel then stores through plain pointers)
+  if (dq_dtype == dtype)
+    if (int e = make_tmap_bshd(&tdq, dq, dtype, B, Sq, Hq, D, dq_strides, 128, "dq")) return e;
   fa2::DqParams d{};
   d.lse = lse; d.delta = delta; d.dq = dq;
   d.sched = static_cast<int*>(workspace);
@@ -274,7 +313,12 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
 
 #ifdef FA2_TRACE
 int fa2_sm100_debug_fetch_trace(int which, long long* host, size_t n) {
-  return static_cast<int>(which == 0 ? fa2::fetch_fwd_trace(host, n) : (which == 1 ? fa2::fetch_bwd_trace(host, n) : fa2::fetch_dq_trace(host, n)));
+  switch (which) {
+    case 0: return static_cast<int>(fa2::fetch_fwd_trace(host, n));
+    case 1: return static_cast<int>(fa2::fetch_bwd_trace(host, n));
+    case 2: return static_cast<int>(fa2::fetch_dq_trace(host, n));
+    default: return static_cast<int>(fa2::fetch_dkdv_trace(host, n));
+  }
 }
 #endif
 
@@ -282,7 +326,7 @@ int fa2_sm100_debug_umma_probe(const void* a, const void* b, float* d, int N, in
                                void* stream) {
   if (!is_16bit(dtype)) return fail(FA2_E_UNSUPPORTED_DTYPE, "dtype code %d", dtype);
   if ((N != 64 && N != 128) || (K != 64 && K != 128)) return fail(FA2_E_BAD_SHAPE, "N and K must be 64 or 128");
-  if (a_mode < 0 || a_mode > 2 || b_mode < 0 || b_mode > 1) return fail(FA2_E_BAD_SHAPE, "bad operand mode");
+  if (a_mode < 0 || a_mode > 4 || b_mode < 0 || b_mode > 1) return fail(FA2_E_BAD_SHAPE, "bad operand mode");
   if (!a || !b || !d) return fail(FA2_E_NULL_POINTER, "null pointer");
   CUtensorMap ta, tb;
   // A as [1, 128, 1, K]: strides (batch, head, seq) = (128*K, K, K)

@@ -1,0 +1,496 @@
+// dK / dV kernel of the deterministic backward for sm_100a (B200), optionally spilling dS for the dQ kernel.
+//
+// Replaces the "pid < NUM_BLOCKS_KV" half of the reference's `_bwd_kernel` (src/backward/kernel.py:65-153):
+// `_compute_column_blocks_dkdv` / `_compute_single_block_dkdv` (src/backward/compute_dkdv.py:116-296, 8-112).
+// One CTA owns a 128-row K/V block and walks the query blocks that see it.
+//
+// Arithmetic: S^T = K Q^T, P^T = exp2(S^T c - LSE2), dV += P^T dO with P rounded to the input
+// dtype, dP^T = V dO^T, dS^T = P^T o (dP^T - delta) rounded to the input dtype, dK += dS^T Q (scaled by softmax_scale
+// in the epilogue).
+//
+// Shared memory bandwidth is the scarce resource of this kernel, not the tensor pipe: a 128 x 128 x 16 product whose
+// two operands come from shared memory reads 8 KB in its 64 cycles - all of the SM's 128 B/clk - so every operand that
+// can live in tensor memory should (measured: the version of this kernel that staged P^T and dS^T through shared
+// memory, 416 KB of shared-memory traffic per block pair, ran at 1.12-1.28 ms; the one that kept P^T in tensor memory
+// and only dS^T in shared memory, 320 KB, at 0.94-0.97 ms). Here
+//   * P^T (16-bit) overwrites S^T and dS^T (16-bit) overwrites dP^T in tensor memory, each thread in its own columns,
+//     and dV / dK take them as the A operand from there: 256 KB of shared-memory traffic per block pair
+//     (S^T, dP^T: 64 KB each; dV, dK: 32 KB each; the Q and dO tiles arriving by TMA: 64 KB);
+//   * dO is double buffered like Q (the shared memory a dS^T tile would need pays for it);
+//   * kSpill: every thread also writes its slice of dS^T to global memory straight from registers, in a layout made
+//     for that: [16 groups of 8 queries][128 keys][16 B], so that a warp's store instruction covers 512 contiguous
+//     bytes. That is the no-swizzle MN-major operand layout of tcgen05.mma, so bwd_dq_spill_sm100.cu bulk-copies the
+//     32 KB tile into shared memory as it is and forms dQ with ONE product per block pair in a fixed order - the
+//     deterministic backward then costs 5 products per pair like the atomic one, not 7.
+//
+// CTA = kCmpWgs compute warpgroups + one issue warpgroup:
+//   compute : thread = key row (TMEM lane), warpgroup g owns query columns [g * 128 / kCmpWgs, ...)
+//   issue   : warp 0 MMA issuer, warp 1 TMA producer, warps 2-3 idle
+// TMEM (512 columns): S^T / P^T [0,128) | dP^T / dS^T [128,256) | dV [256,256+D) | dK [384,384+D)
+// Tensor-pipe order per query block i:  dV(i) | S^T(i+1) | dK(i) | dP^T(i+1)
+#include "fa2_kernels.cuh"
+#include "ptx.cuh"
+
+namespace fa2 {
+
+#ifdef FA2_TRACE
+__device__ long long g_dkdv_trace[4 * 64 * 8];
+#define FA2_STAMP(role, it, ev)                                                                          \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 64)                               \
+      g_dkdv_trace[((role) * 64 + (it)) * 8 + (ev)] = clock64();                                         \
+  } while (0)
+cudaError_t fetch_dkdv_trace(long long* host, size_t n) {
+  return cudaMemcpyFromSymbol(host, g_dkdv_trace, n * sizeof(long long));
+}
+#else
+#define FA2_STAMP(role, it, ev) do { } while (0)
+#endif
+
+namespace {
+
+constexpr int kBlk = 128;
+#ifndef FA2_DKDV_WGS
+#define FA2_DKDV_WGS 4
+#endif
+constexpr int kCmpWgs = FA2_DKDV_WGS;     // compute warpgroups (2 or 4)
+constexpr int kCmpCols = kBlk / kCmpWgs;  // query columns per compute thread
+constexpr int kCmpThreads = kCmpWgs * 128;
+constexpr int kThreads = kCmpThreads + 128;
+constexpr int kMmaWarp = kCmpWgs * 4, kTmaWarp = kMmaWarp + 1;
+// register pool: 640 threads x 96 (launch bound) = 61440 = 4 x 128 x 104 + 128 x 64
+//                384 threads x 168               = 64512 = 2 x 128 x 208 + 128 x 88
+constexpr int kRegsCmp = kCmpWgs == 4 ? 104 : 208;
+constexpr int kRegsIssue = kCmpWgs == 4 ? 64 : 88;
+constexpr int kQStages = 3;   // Q (+LSE) ring: Q(i) lives from S^T(i) to dK(i), and Q(i+1) is wanted right after dV(i)
+constexpr int kDoStages = 2;  // dO (+delta) ring
+#ifndef FA2_DKDV_EMUL
+#define FA2_DKDV_EMUL 1  // every other pair of exponentials on the FMA pipes (ex2_emul2_neg)
+#endif
+
+template <int D>
+struct DkdvSmem {
+  static constexpr int kTileBytes = kBlk * D * 2;  // K, V, Q, dO tiles
+  static constexpr int kKOff = 0;
+  static constexpr int kVOff = kKOff + kTileBytes;
+  static constexpr int kQOff = kVOff + kTileBytes;
+  static constexpr int kDOOff = kQOff + kQStages * kTileBytes;
+  static constexpr int kLseOff = kDOOff + kDoStages * kTileBytes;   // kQStages x 512 B (rides with Q)
+  static constexpr int kDeltaOff = kLseOff + kQStages * kBlk * 4;   // kDoStages x 512 B (rides with dO)
+  static constexpr int kBarOff = kDeltaOff + kDoStages * kBlk * 4;
+  static constexpr int kNumBars = 16;
+  static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
+  static constexpr int kBytes = kTmemSlotOff + 16;
+  static_assert(kBytes <= 232448, "dK/dV kernel smem budget exceeded");
+};
+
+enum DkdvBar {
+  kKvFull = 0,
+  kQFull = 1,     // [3]
+  kQEmpty = 4,    // [3]
+  kDoFull = 7,    // [2]
+  kDoEmpty = 9,   // [2]
+  kSFull = 11,    // S^T(i) is in tensor memory
+  kPFull = 12,    // P^T(i) is in tensor memory (over S^T)
+  kDpFull = 13,
+  kDsFull = 14,   // dS^T(i) is in tensor memory (over dP^T)
+  kDkvFull = 15,
+};
+
+// streaming 16-byte store (written once, read once by the dQ kernel: evict first)
+__device__ __forceinline__ void st_global_cs_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+}  // namespace
+
+template <int D, bool kBf16, bool kSpill>
+__global__ void __launch_bounds__(kThreads, 1)
+fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                    const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
+                    const DkdvParams p) {
+  using L = DkdvSmem<D>;
+  constexpr int kSub = D / 64;
+  constexpr int kSubBytes = kBlk * 128;  // [128 rows x 64 x 16-bit]
+  constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
+  constexpr int kPairs = kCmpCols / 2;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem + L::kKOff;
+  uint8_t* sV = smem + L::kVOff;
+  uint8_t* sQ = smem + L::kQOff;
+  uint8_t* sDO = smem + L::kDOOff;
+  float* sLse = reinterpret_cast<float*>(smem + L::kLseOff);
+  float* sDelta = reinterpret_cast<float*>(smem + L::kDeltaOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_kv_blocks = (p.Sk + kBlk - 1) / kBlk;
+  const int n_q_blocks = (p.Sq + kBlk - 1) / kBlk;
+  const int nblk = static_cast<int>(blockIdx.x);  // causal: low key blocks are seen by the most query blocks - longest first
+  const int head_kv = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int group = p.Hq / p.Hkv;
+  const int shift = p.Sk - p.Sq;
+  const int kv0 = nblk * kBlk;
+
+  // first query block that sees this key block (bottom-right aligned causal mask)
+  int m_start = 0;
+  if (p.causal) m_start = max(0, (kv0 - shift) / kBlk);
+  const int m_count = max(0, n_q_blocks - m_start);
+  const int T = m_count * group;  // iterations: (head in group) x (query block)
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dk);
+    tma_prefetch_desc(&tmap_dv);
+  }
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      mbar_init(&bars[kKvFull], 1);
+      for (int s = 0; s < kQStages; ++s) {
+        mbar_init(&bars[kQFull + s], 1);
+        mbar_init(&bars[kQEmpty + s], 1);
+      }
+      for (int s = 0; s < kDoStages; ++s) {
+        mbar_init(&bars[kDoFull + s], 1);
+        mbar_init(&bars[kDoEmpty + s], 1);
+      }
+      mbar_init(&bars[kSFull], 1);
+      mbar_init(&bars[kPFull], kCmpThreads);
+      mbar_init(&bars[kDpFull], 1);
+      mbar_init(&bars[kDsFull], kCmpThreads);
+      mbar_init(&bars[kDkvFull], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  // whole-TMEM allocation => base 0; the literal keeps tcgen05 addresses warp-uniform for ptxas (see fwd_sm100.cu)
+  if (*tmem_slot != 0u) __trap();
+
+  if (warp >= kMmaWarp) {
+    reg_dealloc<kRegsIssue>();
+    if (warp == kTmaWarp) {
+      // ========================================= TMA producer ========================================
+      if (T > 0 && elect_one()) {
+        mbar_arrive_expect_tx(&bars[kKvFull], 2 * L::kTileBytes);
+        for (int j = 0; j < kSub; ++j) {
+          tma_load_4d(sK + j * kSubBytes, &tmap_k, &bars[kKvFull], j * 64, kv0, head_kv, batch);
+          tma_load_4d(sV + j * kSubBytes, &tmap_v, &bars[kKvFull], j * 64, kv0, head_kv, batch);
+        }
+        for (int it = 0; it < T; ++it) {
+          const int qs = it % kQStages, ds = it % kDoStages;
+          const uint32_t qph = (it / kQStages) & 1, dph = (it / kDoStages) & 1;
+          const int head = head_kv * group + it / m_count;
+          const int m = m_start + it % m_count;
+          const int64_t row_off = (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
+          // Q(it) + its LSE row: released by dK(it - 3)
+          mbar_wait(&bars[kQEmpty + qs], qph ^ 1);
+          mbar_arrive_expect_tx(&bars[kQFull + qs], L::kTileBytes + kBlk * 4);
+          for (int j = 0; j < kSub; ++j)
+            tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, &tmap_q, &bars[kQFull + qs], j * 64, m * kBlk, head, batch);
+          bulk_load_1d(sLse + qs * kBlk, p.lse + row_off, kBlk * 4, &bars[kQFull + qs]);
+          // dO(it) + its delta row: released by dV(it - 2)
+          mbar_wait(&bars[kDoEmpty + ds], dph ^ 1);
+          mbar_arrive_expect_tx(&bars[kDoFull + ds], L::kTileBytes + kBlk * 4);
+          for (int j = 0; j < kSub; ++j)
+            tma_load_4d(sDO + ds * L::kTileBytes + j * kSubBytes, &tmap_do, &bars[kDoFull + ds], j * 64, m * kBlk, head, batch);
+          bulk_load_1d(sDelta + ds * kBlk, p.delta + row_off, kBlk * 4, &bars[kDoFull + ds]);
+        }
+      }
+    } else if (warp == kMmaWarp) {
+      // ========================================== MMA issuer =========================================
+      if (T > 0 && elect_one()) {
+        constexpr uint32_t idesc_kk = make_idesc_f16(kBlk, kBlk, kBf16, false, false);  // S^T, dP^T
+        constexpr uint32_t idesc_tn = make_idesc_f16(kBlk, D, kBf16, false, true);      // dV, dK
+        // K-major views (rows of the tile are the M/N index, the reduction runs along the 128-byte rows)
+        const SmemDesc k_kmaj = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+        const SmemDesc v_kmaj = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+        const SmemDesc q_kmaj = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+        const SmemDesc do_kmaj = make_smem_desc_sw128(smem_u32(sDO), 16, 1024);
+        // MN-major views (rows of the tile are the reduction index)
+        const SmemDesc q_mn = make_smem_desc_sw128(smem_u32(sQ), kSubBytes, 1024);
+        const SmemDesc do_mn = make_smem_desc_sw128(smem_u32(sDO), kSubBytes, 1024);
+
+        // [128 x D] x [128 x D]^T, both K-major, reduction over D
+        auto issue_kmajor = [&](uint32_t d_tmem, SmemDesc a, SmemDesc b) {
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
+            umma_ss(d_tmem, advance(a, off), advance(b, off), idesc_kk, k > 0 ? 1u : 0u);
+          }
+        };
+        // [128 kv x 128 q] (P^T or dS^T, 16-bit, in tensor memory) x [128 q x D] (dO or Q, MN-major), reduction over q.
+        // Compute warpgroup g packed its kCmpCols query columns (k-steps g * kCmpCols / 16 ...) into the first
+        // kCmpCols / 2 columns of its slice.
+        auto issue_acc = [&](uint32_t d_tmem, uint32_t a_tmem, SmemDesc b_mn, bool accumulate) {
+#pragma unroll
+          for (int k = 0; k < kBlk / 16; ++k) {
+            constexpr int kStepsPerWg = kCmpCols / 16;
+            const uint32_t a_col = (k / kStepsPerWg) * kCmpCols + (k % kStepsPerWg) * 8;
+            umma_ts(d_tmem, a_tmem + a_col, advance(b_mn, k * 2048), idesc_tn, (accumulate || k > 0) ? 1u : 0u);
+          }
+        };
+
+        mbar_wait(&bars[kKvFull], 0);
+        mbar_wait(&bars[kQFull + 0], 0);
+        tcgen05_fence_after();
+        issue_kmajor(kTmemS, k_kmaj, q_kmaj);  // S^T(0) = K Q(0)^T
+        umma_commit(&bars[kSFull]);
+        mbar_wait(&bars[kDoFull + 0], 0);
+        tcgen05_fence_after();
+        issue_kmajor(kTmemDP, v_kmaj, do_kmaj);  // dP^T(0) = V dO(0)^T
+        umma_commit(&bars[kDpFull]);
+
+        for (int it = 0; it < T; ++it) {
+          const uint32_t par = it & 1;
+          const int qs = it % kQStages, qsn = (it + 1) % kQStages;
+          const int ds = it % kDoStages, dsn = (it + 1) % kDoStages;
+          const uint32_t qphn = ((it + 1) / kQStages) & 1, dphn = ((it + 1) / kDoStages) & 1;
+          // dV += P^T(it) dO(it)
+          mbar_wait(&bars[kPFull], par);
+          tcgen05_fence_after();
+          FA2_STAMP(2, it, 0);
+          issue_acc(kTmemDV, kTmemS, advance(do_mn, ds * L::kTileBytes), it > 0);
+          umma_commit(&bars[kDoEmpty + ds]);  // dO(it) has fed dP(it) and dV(it)
+          FA2_STAMP(2, it, 1);
+          // S^T(it+1) = K Q(it+1)^T (overwrites P^T(it): the tensor pipe executes in issue order)
+          if (it + 1 < T) {
+            mbar_wait(&bars[kQFull + qsn], qphn);
+            tcgen05_fence_after();
+            issue_kmajor(kTmemS, k_kmaj, advance(q_kmaj, qsn * L::kTileBytes));
+            umma_commit(&bars[kSFull]);
+          }
+          FA2_STAMP(2, it, 2);
+          // dK += dS^T(it) Q(it)
+          mbar_wait(&bars[kDsFull], par);
+          tcgen05_fence_after();
+          FA2_STAMP(2, it, 3);
+          issue_acc(kTmemDK, kTmemDP, advance(q_mn, qs * L::kTileBytes), it > 0);
+          umma_commit(&bars[kQEmpty + qs]);  // Q(it) has fed S(it) and dK(it)
+          FA2_STAMP(2, it, 4);
+          // dP^T(it+1) = V dO(it+1)^T (overwrites dS^T(it))
+          if (it + 1 < T) {
+            mbar_wait(&bars[kDoFull + dsn], dphn);
+            tcgen05_fence_after();
+            issue_kmajor(kTmemDP, v_kmaj, advance(do_kmaj, dsn * L::kTileBytes));
+            umma_commit(&bars[kDpFull]);
+          }
+          FA2_STAMP(2, it, 5);
+        }
+        umma_commit(&bars[kDkvFull]);
+      }
+    }
+  } else {
+    // ====================================== compute warpgroups =====================================
+    reg_alloc<kRegsCmp>();
+    const int wg = warp >> 2;
+    const int r = threadIdx.x & 127;  // key row inside the block == TMEM lane
+    const int kv = kv0 + r;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = lane_sel + kTmemS + wg * kCmpCols;   // P^T (16-bit) goes over the head of the same columns
+    const uint32_t tDP = lane_sel + kTmemDP + wg * kCmpCols;  // ... and dS^T over the head of these
+    const float2 neg_c2 = make_float2(-p.scale_log2, -p.scale_log2);
+    // spill: this thread's 16-byte pieces of dS^T(m, n) go to [piece = 8 queries][key row][16 B] inside the 32 KB tile,
+    // so that one warp store covers 512 contiguous bytes. (A dedicated spill warpgroup reading dS^T back from tensor
+    // memory was slower: 1.09 ms against 1.02 - four warps do not keep the 32 B/clk/SM store path busy.)
+    uint8_t* spill_row = nullptr;
+    long long prefix = 0;
+    if (kSpill) spill_row = static_cast<uint8_t*>(p.ds_spill) + (static_cast<size_t>(wg) * (kCmpCols / 8) * kBlk + r) * 16;
+
+    for (int it = 0; it < T; ++it) {
+      const uint32_t par = it & 1;
+      const int qs = it % kQStages, ds = it % kDoStages;
+      const uint32_t qph = (it / kQStages) & 1, dph = (it / kDoStages) & 1;
+      const int j_in_head = it % m_count;
+      const int m = m_start + j_in_head;
+      const int q0 = m * kBlk + wg * kCmpCols;  // first query column of this thread's slice
+      const float4* lse_s = reinterpret_cast<const float4*>(sLse + qs * kBlk + wg * kCmpCols);
+      const float4* delta_s = reinterpret_cast<const float4*>(sDelta + ds * kBlk + wg * kCmpCols);
+      const bool need_mask = (kv0 + kBlk > p.Sk) || (m * kBlk + kBlk > p.Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
+
+      // ---- P^T = exp2(S^T * c - LSE) = exp2(-(LSE - S^T * c)) ----
+      if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 0);
+      mbar_wait(&bars[kQFull + qs], qph);  // the LSE row travels with Q
+      mbar_wait(&bars[kSFull], par);
+      tcgen05_fence_after();
+      if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 1);
+      uint32_t su[kCmpCols];
+#pragma unroll
+      for (int h = 0; h < kCmpCols / 32; ++h) tmem_ld_32x32b_x32(tS + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[h * 32]));
+      tmem_wait_ld();
+      float2 pf[kPairs];  // probabilities, fp32, pairs of neighbouring query columns
+#pragma unroll
+      for (int j4 = 0; j4 < kCmpCols / 4; ++j4) {
+        const float4 l4 = lse_s[j4];
+        const int j = j4 * 4;
+        const float2 t0 = ffma2(make_float2(__uint_as_float(su[j]), __uint_as_float(su[j + 1])), neg_c2, make_float2(l4.x, l4.y));
+        const float2 t1 = ffma2(make_float2(__uint_as_float(su[j + 2]), __uint_as_float(su[j + 3])), neg_c2, make_float2(l4.z, l4.w));
+        // a fully masked query row carries LSE = -inf: exp2(+inf) = inf here, replaced by 0 in the masked path below
+        // (such rows only occur in blocks that need masking)
+        pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
+        if (FA2_DKDV_EMUL) pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
+        else pf[j4 * 2 + 1] = make_float2(ex2_approx(-t1.x), ex2_approx(-t1.y));
+      }
+      if (need_mask) {
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) {
+          const int qi = q0 + 2 * j;
+          const bool row_ok = kv < p.Sk;
+          const bool ok0 = row_ok && (qi < p.Sq) && (!p.causal || kv <= qi + shift);
+          const bool ok1 = row_ok && (qi + 1 < p.Sq) && (!p.causal || kv <= qi + 1 + shift);
+          pf[j].x = ok0 ? pf[j].x : 0.f;
+          pf[j].y = ok1 ? pf[j].y : 0.f;
+        }
+      }
+      {
+        uint32_t pk[kPairs];
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) pk[j] = pack2<kBf16>(pf[j].x, pf[j].y);
+        if constexpr (kPairs == 16) tmem_st_32x32b_x16(tS, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+        else tmem_st_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_wait_st();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&bars[kPFull]);
+      if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 2);
+
+      // ---- dS^T = P^T o (dP^T - delta) ----
+      mbar_wait(&bars[kDoFull + ds], dph);  // the delta row travels with dO
+      mbar_wait(&bars[kDpFull], par);
+      tcgen05_fence_after();
+      if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 3);
+      uint32_t dpu[kCmpCols];
+#pragma unroll
+      for (int h = 0; h < kCmpCols / 32; ++h) tmem_ld_32x32b_x32(tDP + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&dpu[h * 32]));
+      tmem_wait_ld();
+      uint32_t w[kPairs];
+#pragma unroll
+      for (int j4 = 0; j4 < kCmpCols / 4; ++j4) {
+        const float4 d4 = delta_s[j4];
+        const int j = j4 * 4;
+        const float2 x0 = fsub2(make_float2(__uint_as_float(dpu[j]), __uint_as_float(dpu[j + 1])), make_float2(d4.x, d4.y));
+        const float2 x1 = fsub2(make_float2(__uint_as_float(dpu[j + 2]), __uint_as_float(dpu[j + 3])), make_float2(d4.z, d4.w));
+        const float2 s0 = fmul2(pf[j4 * 2], x0);
+        const float2 s1 = fmul2(pf[j4 * 2 + 1], x1);
+        w[j4 * 2] = pack2<kBf16>(s0.x, s0.y);
+        w[j4 * 2 + 1] = pack2<kBf16>(s1.x, s1.y);
+      }
+      if constexpr (kPairs == 16) tmem_st_32x32b_x16(tDP, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
+      else tmem_st_32x32b_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&w[0]));
+      tmem_wait_st();
+      tcgen05_fence_before();
+      mbar_arrive(&bars[kDsFull]);
+      if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 4);
+
+      if (kSpill) {
+        const int head = head_kv * group + it / m_count;
+        if (j_in_head == 0) prefix = ds_tile_prefix(m_start, p.Sq, p.Sk, p.causal);
+        const long long tile = (static_cast<long long>(batch) * p.Hq + head) * p.tiles_per_head + prefix + nblk;
+        prefix += visible_kv_blocks_of(m, p.Sq, p.Sk, p.causal);
+        uint8_t* dst = spill_row + tile * kDsTileBytes;
+#pragma unroll
+        for (int c = 0; c < kCmpCols / 8; ++c)
+          st_global_cs_v4(dst + c * (kBlk * 16), w[c * 4], w[c * 4 + 1], w[c * 4 + 2], w[c * 4 + 3]);
+      }
+    }
+
+    // ---- epilogue: dK * scale, dV -> smem (the K / V tiles are dead once every MMA retired) -> TMA store ----
+    if (T > 0) {
+      mbar_wait(&bars[kDkvFull], 0);
+      tcgen05_fence_after();
+    }
+    constexpr int kChunksPerOut = D / 32;            // 32-column chunks of dK (and of dV)
+    constexpr int kChunks = 2 * kChunksPerOut;       // warpgroup wg takes chunks wg, wg + 4, ...
+#pragma unroll
+    for (int cc = 0; cc < (kChunks + kCmpWgs - 1) / kCmpWgs; ++cc) {
+      const int chunk = wg + cc * kCmpWgs;
+      if (chunk < kChunks) {
+        const int which = chunk / kChunksPerOut;  // 0: dK, 1: dV
+        const int col = (chunk % kChunksPerOut) * 32;
+        uint8_t* sOut = (which == 0) ? sK : sV;
+        const float mul = (which == 0) ? p.softmax_scale : 1.0f;
+        uint32_t o[32];
+        if (T > 0) {
+          tmem_ld_32x32b_x32(lane_sel + (which == 0 ? kTmemDK : kTmemDV) + col, o);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+        uint8_t* sub = sOut + (col / 64) * kSubBytes;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 v;
+          v.x = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 0]) * mul, __uint_as_float(o[q4 * 8 + 1]) * mul);
+          v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * mul, __uint_as_float(o[q4 * 8 + 3]) * mul);
+          v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * mul, __uint_as_float(o[q4 * 8 + 5]) * mul);
+          v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * mul, __uint_as_float(o[q4 * 8 + 7]) * mul);
+          *reinterpret_cast<uint4*>(sub + sw128_offset(r, ((col % 64) / 8) + q4)) = v;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, kCmpThreads);
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < kSub; ++j) {
+        tma_store_4d(&tmap_dk, sK + j * kSubBytes, j * 64, kv0, head_kv, batch);
+        tma_store_4d(&tmap_dv, sV + j * kSubBytes, j * 64, kv0, head_kv, batch);
+      }
+      bulk_commit_group();
+      bulk_wait_group_read<0>();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(0u);
+  }
+}
+
+template <int D, bool kBf16, bool kSpill>
+static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                     const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
+                                     const DkdvParams& p, cudaStream_t stream) {
+  auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill>;
+  constexpr int smem = DkdvSmem<D>::kBytes;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv, p.B);
+  kernel<<<grid, kThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
+                            const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk,
+                            const CUtensorMap& tdv, const DkdvParams& p, cudaStream_t stream) {
+#define FA2_DKDV_CASE(DD, BF, SP) \
+  if (D == DD && bf16 == BF && spill == SP) return launch_bwd_dkdv_t<DD, BF, SP>(tq, tk, tv, tdo, tdk, tdv, p, stream);
+  FA2_DKDV_CASE(128, true, true) FA2_DKDV_CASE(128, true, false) FA2_DKDV_CASE(128, false, true) FA2_DKDV_CASE(128, false, false)
+  FA2_DKDV_CASE(64, true, true) FA2_DKDV_CASE(64, true, false) FA2_DKDV_CASE(64, false, true) FA2_DKDV_CASE(64, false, false)
+#undef FA2_DKDV_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace fa2

@@ -74,6 +74,63 @@ struct DqParams {
 cudaError_t launch_bwd_dq(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           const CUtensorMap& tdo, const CUtensorMap& tdq, const DqParams& p, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------
+// deterministic backward with spilled dS (bwd_dkdv_sm100.cu, bwd_dq_spill_sm100.cu)
+// ---------------------------------------------------------------------------------------------
+// The dK/dV kernel writes every dS^T tile it forms (128 keys x 128 queries, 16-bit = 32 KB, laid out as
+// [16 groups of 8 queries][128 keys][16 B]: coalesced to write from registers and directly usable as a no-swizzle
+// MN-major tcgen05.mma operand) to a workspace; the dQ kernel then only has to form dQ = sum_n dS(m, n) K(n) - one
+// product per block pair instead of three, in a fixed order.
+// Workspace layout: [B][Hq][visible (m, n) pairs, m-major][32 KB]; the tiles of one query block are contiguous.
+constexpr int kDsTileBytes = 128 * 128 * 2;
+
+// key blocks (128 rows) visible to query block m under the bottom-right aligned causal mask
+__host__ __device__ inline int visible_kv_blocks_of(int m, int Sq, int Sk, int causal) {
+  const int row0 = m * 128;
+  if (row0 >= Sq) return 0;
+  const int last_row = (row0 + 128 < Sq ? row0 + 128 : Sq) - 1;
+  int cols = Sk;
+  if (causal && last_row + Sk - Sq + 1 < cols) cols = last_row + Sk - Sq + 1;
+  return cols <= 0 ? 0 : (cols + 127) / 128;
+}
+// number of spilled tiles that precede query block m inside one (batch, head)
+__host__ __device__ inline long long ds_tile_prefix(int m, int Sq, int Sk, int causal) {
+  if (!causal) return static_cast<long long>(m) * ((Sk + 127) / 128);
+  long long s = 0;
+  for (int i = 0; i < m; ++i) s += visible_kv_blocks_of(i, Sq, Sk, causal);
+  return s;
+}
+
+// dK / dV kernel of the deterministic backward; `ds_spill` != nullptr: also write the dS tiles
+struct DkdvParams {
+  const float* lse;    // [B, Hq, lse_stride] log2 domain
+  const float* delta;  // [B, Hq, lse_stride]
+  void* ds_spill;      // workspace described above, or nullptr
+  long long tiles_per_head;
+  int B, Hq, Hkv, Sq, Sk;
+  int lse_stride;
+  float softmax_scale;
+  float scale_log2;
+  int causal;
+};
+cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
+                            const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk,
+                            const CUtensorMap& tdv, const DkdvParams& p, cudaStream_t stream);
+
+// dQ from the spilled dS tiles: persistent, one product per block pair, HBM-bound (reads every tile once)
+struct DqSpillParams {
+  const void* ds_spill;
+  long long tiles_per_head;
+  int* sched;          // work-item counter, 0 on entry (the kernel re-zeroes it)
+  void* dq;            // [B, Sq, Hq, D]
+  int64_t dq_strides[3];
+  int dq_is_16bit;
+  int B, Hq, Hkv, Sq, Sk;
+  float softmax_scale;
+  int causal;
+};
+cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream);
+
 struct DqConvertParams {
   const float* dq_accum;  // as written by the backward kernel
   void* dq;               // [B, Sq, Hq, D] with strides below
@@ -106,6 +163,7 @@ cudaError_t launch_probe(bool bf16, const CUtensorMap& ta, const CUtensorMap& tb
 cudaError_t fetch_fwd_trace(long long* host, size_t n);
 cudaError_t fetch_bwd_trace(long long* host, size_t n);
 cudaError_t fetch_dq_trace(long long* host, size_t n);
+cudaError_t fetch_dkdv_trace(long long* host, size_t n);
 #endif
 
 }  // namespace fa2

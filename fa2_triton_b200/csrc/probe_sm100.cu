@@ -50,6 +50,14 @@ fa2_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       *reinterpret_cast<uint4*>(sA + (c / 8) * (K * 128) + sw128_offset(k, c % 8)) = v;
     }
     fence_proxy_async_smem();
+  } else if (p.a_mode == 3 || p.a_mode == 4) {
+    // global [K, 128] row-major -> smem MN-major, no swizzle: 16 slabs (8 M-elements each) of [K rows x 16 bytes]
+    for (int idx = tid; idx < K * 16; idx += 128) {
+      const int k = idx / 16, c = idx % 16;
+      const uint4 v = *reinterpret_cast<const uint4*>(ga + k * 128 + c * 8);
+      *reinterpret_cast<uint4*>(sA + c * (K * 16) + k * 16) = v;
+    }
+    fence_proxy_async_smem();
   } else if (p.a_mode == 2) {
     // global [128, K] row-major -> TMEM columns [256, 256 + K/2), lane == row, two 16-bit values per column
     for (int c0 = 0; c0 < K / 2; c0 += 32) {
@@ -79,7 +87,7 @@ fa2_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     mbar_wait(load_bar, 0);
     tcgen05_fence_after();
 
-    const uint32_t idesc = make_idesc_f16(128, N, kBf16, p.a_mode == 1, p.b_mode == 1);
+    const uint32_t idesc = make_idesc_f16(128, N, kBf16, p.a_mode == 1 || p.a_mode >= 3, p.b_mode == 1);
     const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
     for (int k = 0; k < K / 16; ++k) {
       SmemDesc bdesc;
@@ -93,6 +101,10 @@ fa2_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         SmemDesc adesc;
         if (p.a_mode == 0)
           adesc = make_smem_desc_sw128(a_addr + (k / 4) * 16384 + (k % 4) * 32, 16, 1024);
+        else if (p.a_mode == 3)  // LBO: 8-row groups along K (128 B apart), SBO: 8-element groups along M (slabs)
+          adesc = make_smem_desc_noswizzle(a_addr + k * 256, 128, K * 16);
+        else if (p.a_mode == 4)  // the other reading of LBO / SBO (expected to be wrong; kept for the probe script)
+          adesc = make_smem_desc_noswizzle(a_addr + k * 256, K * 16, 128);
         else
           adesc = make_smem_desc_sw128(a_addr + k * 2048, K * 128, 1024);
         umma_ss(tmem_base, adesc, bdesc, idesc, k > 0);

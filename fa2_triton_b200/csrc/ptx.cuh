@@ -241,6 +241,33 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* sme
                : "memory");
 }
 
+// linear bulk copies (no tensor map): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
 // wait until at most N committed bulk groups still have pending smem *reads*
@@ -293,6 +320,18 @@ __device__ __forceinline__ SmemDesc make_smem_desc_sw128(uint32_t smem_addr, uin
   SmemDesc d;
   d.lo = ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
   d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return d;
+}
+
+// No swizzle ("interleave"): the operand is a grid of 8 x 16-byte core matrices, each stored as 128 contiguous bytes.
+//   K-major : core matrix = 8 MN-rows x 8 K-elements;  LBO = byte distance between core matrices along K,
+//             SBO = along MN.
+//   MN-major: core matrix = 8 K-rows x 8 MN-elements;  LBO = byte distance between core matrices along K (8-row
+//             groups), SBO = along MN (8-element groups)  - pinned by tests/test_umma_probe.py (a_mode 3).
+__device__ __forceinline__ SmemDesc make_smem_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  SmemDesc d;
+  d.lo = ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
   return d;
 }
 

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 5
+#define FA2_SM100_ABI_VERSION 6
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -51,6 +51,12 @@ extern "C" {
 #define FA2_DQ_FUSED_ORDERED 2  /* fused kernel, adds serialised per query tile by a ticket (bit-repeatable, slowest) */
 #define FA2_DQ_NONE 3           /* dK and dV only (q does not require a gradient); dq may be NULL */
 #define FA2_DQ_ONLY 4           /* dQ only, deterministic kernel (k, v do not require gradients); dk, dv may be NULL */
+#define FA2_DQ_DET_SPILL 5      /* deterministic, 5 products per block pair: the dK/dV kernel also writes its 16-bit dS tiles
+                                   to the workspace and the dQ kernel sums dS K over them in a fixed key-block order
+                                   (no recomputation, no atomics; workspace = 32 KB per visible 128 x 128 block pair) */
+#define FA2_DQ_SPILL_DKDV 6     /* first half of mode 5 alone: dK, dV and the dS tiles (dq may be NULL) */
+#define FA2_DQ_SPILL_DQ 7       /* second half of mode 5 alone: dQ from the tiles a mode 5 / 6 call left in `workspace`
+                                   with the same shapes (dk, dv may be NULL) */
 
 #define FA2_E_UNSUPPORTED_HEAD_DIM (-1)
 #define FA2_E_UNSUPPORTED_DTYPE (-2)
@@ -80,14 +86,16 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
 
 /* Bytes of scratch fa2_sm100_bwd needs. FA2_DQ_ATOMIC / FA2_DQ_FUSED_ORDERED: the fp32 dQ accumulator plus one int per
  * (batch, head, 128-row query tile). FA2_DQ_DETERMINISTIC / FA2_DQ_ONLY: 256 bytes (work-item counter of the
- * persistent dQ kernel; cleared by the call itself). FA2_DQ_NONE: 0. The workspace must be 16-byte aligned. */
-size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int deterministic);
+ * persistent dQ kernel; cleared by the call itself). FA2_DQ_DET_SPILL (and 6, 7): 1 KB + B * Hq * (visible block pairs) * 32 KB
+ * (`causal` decides which pairs are visible; B=4, H=32, S=4096 causal: 2.06 GiB). FA2_DQ_NONE: 0.
+ * The workspace must be 16-byte aligned. */
+size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int causal, int deterministic);
 
 /* dQ ([B, Sq, Hq, D], `dq_dtype` = the input dtype or 32 for fp32 as the reference allocates it at
  * src/backward/caller.py:86), dK and dV (input dtype, [B, Sk, Hkv, D], GQA head groups already summed).
  * `deterministic` selects the dQ path (FA2_DQ_*). Modes 0 and 2 need `workspace` all zero on entry: pass it to
- * fa2_sm100_bwd_delta (same stream) or clear it yourself. Modes 1 and 4 clear their 256 bytes themselves; one call
- * per workspace may be in flight at a time. Results of modes 1, 2 and 4 are bit-identical run to run. */
+ * fa2_sm100_bwd_delta (same stream) or clear it yourself. Modes 1, 4 and 5 clear what they need themselves; one call
+ * per workspace may be in flight at a time. Results of modes 1, 2, 4 and 5 are bit-identical run to run. */
 int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
                   const float* lse, const float* delta,
                   void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes,

@@ -30,20 +30,25 @@ def test_library_exports_every_declared_symbol():
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/fa2_sm100.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.fa2_sm100_version() == 5
+    assert lib.fa2_sm100_version() == 6
 
 
 def test_workspace_size_formula():
     from fa2_triton_b200 import _lib
     lib = _lib.load()
     # atomic / fused-ordered: fp32 accumulator over Sq padded to 128 + one ticket per (b, h, tile), 16-byte rounded
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 0) == 4 * 32 * 4096 * 128 * 4 + 4 * 32 * 32 * 4
-    assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 1000, 1000, 64, 2) == 1024 * 64 * 4 + 32
-    assert lib.fa2_sm100_bwd_workspace_bytes(0, 1, 1, 1, 64, 0) == 0
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 0) == 4 * 32 * 4096 * 128 * 4 + 4 * 32 * 32 * 4
+    assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 1000, 1000, 64, 0, 2) == 1024 * 64 * 4 + 32
+    assert lib.fa2_sm100_bwd_workspace_bytes(0, 1, 1, 1, 64, 0, 0) == 0
     # deterministic / dQ only: dQ has its own kernel, nothing to accumulate into - just its scheduler's counter
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1) == 256
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 4) == 256
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 3) == 0
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 1) == 256
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 4) == 256
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 3) == 0
+    # deterministic with spilled dS: 1 KB + one 32 KB tile per visible 128 x 128 block pair
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 5) == 1024 + 4 * 32 * (32 * 33 // 2) * 32768
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 0, 5) == 1024 + 4 * 32 * 32 * 32 * 32768
+    # bottom-right aligned causal mask, Sq = 300 (3 query blocks), Sk = 1000: the blocks see 7, 8 and 8 key blocks
+    assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 300, 1000, 64, 1, 5) == 1024 + (7 + 8 + 8) * 32768
 
 
 def test_argument_errors_need_no_gpu():
