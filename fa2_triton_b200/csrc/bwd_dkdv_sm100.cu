@@ -129,7 +129,6 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int n_kv_blocks = (p.Sk + kBlk - 1) / kBlk;
   const int n_q_blocks = (p.Sq + kBlk - 1) / kBlk;
   const int nblk = static_cast<int>(blockIdx.x);  // causal: low key blocks are seen by the most query blocks - longest first
   const int head_kv = blockIdx.y;
@@ -309,6 +308,13 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // memory was slower: 1.09 ms against 1.02 - four warps do not keep the 32 B/clk/SM store path busy.)
     uint8_t* spill_row = nullptr;
     long long prefix = 0;
+    // The store path takes ~32 B/clk/SM: the 32 KB of a block pair occupy it for >= 1000 cycles, and a warp that issues
+    // its four stores back to back sits in them for most of that. So every thread writes half of its pieces right
+    // after handing dS^T over and carries the other half to the same point after P^T of the next block - each time
+    // just before a barrier it would have to wait at anyway.
+    constexpr int kPieces = kCmpCols / 8;
+    uint32_t carry[kPieces / 2 * 4];
+    uint8_t* carry_dst = nullptr;
     if (kSpill) spill_row = static_cast<uint8_t*>(p.ds_spill) + (static_cast<size_t>(wg) * (kCmpCols / 8) * kBlk + r) * 16;
 
     for (int it = 0; it < T; ++it) {
@@ -367,6 +373,11 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tcgen05_fence_before();
       mbar_arrive(&bars[kPFull]);
       if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 2);
+      if (kSpill && it > 0) {
+#pragma unroll
+        for (int c = 0; c < kPieces / 2; ++c)
+          st_global_cs_v4(carry_dst + (kPieces / 2 + c) * (kBlk * 16), carry[c * 4], carry[c * 4 + 1], carry[c * 4 + 2], carry[c * 4 + 3]);
+      }
 
       // ---- dS^T = P^T o (dP^T - delta) ----
       mbar_wait(&bars[kDoFull + ds], dph);  // the delta row travels with dO
@@ -403,9 +414,17 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         prefix += visible_kv_blocks_of(m, p.Sq, p.Sk, p.causal);
         uint8_t* dst = spill_row + tile * kDsTileBytes;
 #pragma unroll
-        for (int c = 0; c < kCmpCols / 8; ++c)
+        for (int c = 0; c < kPieces / 2; ++c)
           st_global_cs_v4(dst + c * (kBlk * 16), w[c * 4], w[c * 4 + 1], w[c * 4 + 2], w[c * 4 + 3]);
+#pragma unroll
+        for (int j = 0; j < kPieces / 2 * 4; ++j) carry[j] = w[kPieces / 2 * 4 + j];
+        carry_dst = dst;
       }
+    }
+    if (kSpill && T > 0) {
+#pragma unroll
+      for (int c = 0; c < kPieces / 2; ++c)
+        st_global_cs_v4(carry_dst + (kPieces / 2 + c) * (kBlk * 16), carry[c * 4], carry[c * 4 + 1], carry[c * 4 + 2], carry[c * 4 + 3]);
     }
 
     // ---- epilogue: dK * scale, dV -> smem (the K / V tiles are dead once every MMA retired) -> TMA store ----

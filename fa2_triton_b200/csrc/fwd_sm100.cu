@@ -8,13 +8,16 @@
 //   log2-domain online softmax with c = softmax_scale * log2(e); P rounded to the input dtype before PV;
 //   O = (P V) / l in the input dtype;  LSE2 = m + log2(l) in fp32 (src/forward/kernel.py:119,259-272).
 //
-// CTA = 12 warps:
-//   warps 0-3  : softmax warpgroup for Q tile 0 (one thread per query row; TMEM lane == row)
-//   warps 4-7  : softmax warpgroup for Q tile 1
-//   warp  8    : MMA issuer (one elected lane)           warp 9 : TMA producer (one elected lane)
-//   warps 10-11: idle (keep the third warpgroup whole for setmaxnreg)
+// CTA = 2 * kHalves softmax warpgroups + one issue warpgroup (kHalves = FA2_FWD_HALVES, 1 or 2):
+//   softmax warpgroup (t, h): Q tile t, key columns [h * 128 / kHalves, ...) of every block; thread = query row
+//                             (TMEM lane == row). With kHalves = 2 the two threads of a row exchange their block
+//                             maxima through shared memory (one named barrier per block) and keep partial row sums.
+//                             Four softmax warps per scheduler instead of two: the row's 128 exponentials are the
+//                             dependent chain softmax -> PV -> QK(next) of a tile is waiting for, and a lone warp
+//                             only keeps the MUFU ~2/3 busy (measured T_softmax 2100 cycles -> see DESIGN.md).
+//   issue warpgroup: warp 0 MMA issuer (one elected lane), warp 1 TMA producer (one elected lane), 2 idle warps
 // TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,256+D) | O1 [256+D,256+2D).
-//   P_t (16-bit, 64 columns) overwrites the first half of S_t once the owning thread has read its row.
+//   P_t (16-bit) overwrites the head of the S_t columns of the thread that wrote it, once it has read its row.
 #include <type_traits>
 
 #include "fa2_kernels.cuh"
@@ -38,7 +41,23 @@ namespace {
 
 constexpr int kBM = 128;  // query rows per tile (= TMEM lanes)
 constexpr int kBN = 128;  // key rows per block
-constexpr int kFwdThreads = 384;
+// Measured on B200 (B=4, H=32, S=4096, D=128 causal; same box, same call): 1 thread per row 0.566 ms, + speculative
+// exponentials 0.567, 2 threads per row 0.574, 2 threads + speculative 0.643, + a quarter of the exponentials on the FMA
+// pipes 0.637. Shortening the softmax chain does not move the kernel: with ~1 kW drawn it runs at the power cap (SM clock
+// 1.55-1.75 GHz instead of 1.965), so what counts is work per step, not bubbles - the leanest variant is the default.
+#ifndef FA2_FWD_HALVES
+#define FA2_FWD_HALVES 1
+#endif
+constexpr int kHalves = FA2_FWD_HALVES;          // softmax threads per query row
+constexpr int kCols = kBN / kHalves;             // key columns per softmax thread
+constexpr int kSmxThreads = 2 * kHalves * 128;   // softmax threads per CTA
+constexpr int kTileSmxThreads = kHalves * 128;   // ... per Q tile
+constexpr int kFwdThreads = kSmxThreads + 128;
+constexpr int kMmaWarp = kSmxThreads / 32, kTmaWarp = kMmaWarp + 1;
+// register pools (setmaxnreg): 384 threads x 168 = 64512 = 2 x 128 x 208 + 128 x 88
+//                              640 threads x  96 = 61440 = 4 x 128 x 104 + 128 x 64
+constexpr int kRegsSmx = kHalves == 2 ? 104 : 208;
+constexpr int kRegsIssue = kHalves == 2 ? 64 : 88;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between rescales
 // Of every FA2_FWD_EMUL_DEN probabilities, FA2_FWD_EMUL_NUM are exponentiated on the FMA pipes (ex2_emul) and the rest
 // on the MUFU. Measured issue costs per warp instruction and scheduler (scripts/micro/pipe_rates.cu): MUFU.EX2 8 cycles,
@@ -52,9 +71,7 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between
 #ifndef FA2_FWD_EMUL_DEN
 #define FA2_FWD_EMUL_DEN 4
 #endif
-// Speculative exponentials against the previous reference maximum (see the softmax loop). Off by default: measured
-// slower than the two-pass form on B200 (0.77 vs 0.57-0.64 ms) - the block's 128 scores and 64 packed results are
-// live together and the FMNMX no longer hide behind anything.
+// Speculative exponentials against the previous reference maximum (see the softmax loop). Off: no gain (see above).
 #ifndef FA2_FWD_SPEC
 #define FA2_FWD_SPEC 0
 #endif
@@ -70,7 +87,9 @@ struct FwdSmem {
   // barriers: q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full[2]
   static constexpr int kNumBars = 1 + 4 * kStages + 6;
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
-  static constexpr int kBytes = kTmemSlotOff + 16;
+  // row statistics exchanged between the kHalves threads of a row: [parity 2 x kind 2][tile 2][half 2][128 rows] fp32
+  static constexpr int kXchgOff = kTmemSlotOff + 16;
+  static constexpr int kBytes = kXchgOff + 4 * 2 * 2 * kBM * 4;
   static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-byte alignment
 };
 
@@ -109,6 +128,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
+  float* xchg = reinterpret_cast<float*>(smem + L::kXchgOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,13 +144,13 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int nblk1 = num_kv_blocks(row0 + kBM, p.Sq, p.Sk, p.causal);
   const int nblk_max = max(nblk0, nblk1);
 
-  if (warp == 9 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int s = 0; s < kStages; ++s) {
@@ -141,7 +161,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(&s_full[t], 1);
-        mbar_init(&p_full[t], kBM);
+        mbar_init(&p_full[t], kTileSmxThreads);
         mbar_init(&o_full[t], 1);
       }
       fence_barrier_init();
@@ -159,11 +179,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
-  // setmaxnreg at the top of each role branch (ptxas widens the budget only for dominated code):
-  // pool = 384 threads x 168 launch registers = 64512 = 2 softmax warpgroups x 128 x 208 + 1 issue warpgroup x 128 x 88
-  if (warp >= 8) {
-    reg_dealloc<88>();
-  if (warp == 9) {
+  // setmaxnreg at the top of each role branch (ptxas widens the budget only for dominated code)
+  if (warp >= kMmaWarp) {
+    reg_dealloc<kRegsIssue>();
+  if (warp == kTmaWarp) {
     // ======================================= TMA producer =======================================
     if (nblk_max > 0 && elect_one()) {
       const int n_q_tiles = (row0 + kBM < p.Sq) ? 2 : 1;
@@ -184,7 +203,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           tma_load_4d(sV + s * L::kTileBytes + j * kSubBytes, &tmap_v, &v_full[s], j * 64, i * kBN, head_kv, batch);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ======================================== MMA issuer ========================================
     if (nblk_max > 0 && elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kBM, kBN, kBf16, false, false);
@@ -207,7 +226,11 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const SmemDesc va = advance(v_desc, stage * L::kTileBytes);
 #pragma unroll
         for (int k = 0; k < kBN / 16; ++k) {
-          umma_ts(tmem_base + 256 + t * D, tmem_base + t * kBN + k * 8, advance(va, k * 2048), idesc_pv,
+          // softmax thread h of a row packed its kCols probabilities (k-steps h * kCols / 16 ...) into the first
+          // kCols / 2 columns of its own slice of S
+          constexpr int kStepsPerHalf = kCols / 16;
+          const uint32_t a_col = (k / kStepsPerHalf) * kCols + (k % kStepsPerHalf) * 8;
+          umma_ts(tmem_base + 256 + t * D, tmem_base + t * kBN + a_col, advance(va, k * 2048), idesc_pv,
                   (accumulate || k > 0) ? 1u : 0u);
         }
       };
@@ -265,72 +288,91 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   }
   } else {
     // ===================================== softmax warpgroups ====================================
-    reg_alloc<208>();
-    const int t = warp >> 2;
-    const int r = threadIdx.x & 127;  // row inside the tile == TMEM lane
+    reg_alloc<kRegsSmx>();
+    const int t = warp / (4 * kHalves);       // Q tile
+    const int half = (warp >> 2) % kHalves;   // which kCols key columns of every block
+    const int r = threadIdx.x & 127;          // row inside the tile == TMEM lane
     const int tile_row0 = row0 + t * kBM;
     const int row = tile_row0 + r;
     const int nblk = t == 0 ? nblk0 : nblk1;
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + t * kBN;
-    const uint32_t tO = tmem_base + lane_sel + 256 + t * D;
+    const uint32_t tS = tmem_base + lane_sel + t * kBN + half * kCols;  // this thread's scores; P goes over their head
+    constexpr int kOCols = D / kHalves;                                 // columns of O this thread rescales / stores
+    const uint32_t tO = tmem_base + lane_sel + 256 + t * D + half * kOCols;
     const float c = p.scale_log2;
     const int shift = p.Sk - p.Sq;
+    auto xchg_slot = [&](int par, int h, int kind = 0) { return xchg + (((par * 2 + kind) * 2 + t) * 2 + h) * kBM + r; };
 
     float m_ref = -INFINITY;
-    float l = 0.f;
+    float l = 0.f;  // kHalves == 2: the sum over this thread's columns only
 
     for (int i = 0; i < nblk; ++i) {
-      if (r == 0) FA2_STAMP(t, i, 0);
+      if (r == 0 && half == 0) FA2_STAMP(t, i, 0);
       mbar_wait(&s_full[t], i & 1);
       tcgen05_fence_after();
-      if (r == 0) FA2_STAMP(t, i, 1);
+      if (r == 0 && half == 0) FA2_STAMP(t, i, 1);
 
-      uint32_t su[kBN / 32][32];  // raw fp32 bits of this thread's score row
+      float s[kCols];  // this thread's part of the score row
+      auto load_scores = [&]() {
+        uint32_t su[kCols / 32][32];
 #pragma unroll
-      for (int cidx = 0; cidx < kBN / 32; ++cidx) tmem_ld_32x32b_x32(tS + cidx * 32, su[cidx]);
-      tmem_wait_ld();
-      if (r == 0) FA2_STAMP(t, i, 2);
-      float s[kBN];
+        for (int cidx = 0; cidx < kCols / 32; ++cidx) tmem_ld_32x32b_x32(tS + cidx * 32, su[cidx]);
+        tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) s[j] = __uint_as_float(su[j / 32][j % 32]);
+        for (int j = 0; j < kCols; ++j) s[j] = __uint_as_float(su[j / 32][j % 32]);
+      };
+      load_scores();
+      if (r == 0 && half == 0) FA2_STAMP(t, i, 2);
 
-      const int col0 = i * kBN;
-      const int block_last = col0 + kBN - 1;
+      const int col0 = i * kBN + half * kCols;
+      const int block_last = i * kBN + kBN - 1;
       const bool need_mask = (block_last >= p.Sk) || (p.causal && block_last > tile_row0 + shift);
       if (need_mask) {
         const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
 #pragma unroll
-        for (int j = 0; j < kBN; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
+        for (int j = 0; j < kCols; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
       }
 
-      uint32_t pk[kBN / 64][32];
+      uint32_t pk[kCols / 2];
       // Speculative fast path (every block but the first and the masked ones): exponentiate against the current
       // reference maximum right away and find the block maximum on the side - the FMNMX run on the ALU pipe in the
       // shadow of the MUFU. Only if some row of this warp turns out to exceed the reference by more than the rescale
-      // threshold is the block redone the slow way (maximum first, rescale O, exponentiate). Results are identical
-      // to always taking the slow path; the ~500-cycle maximum pass leaves the softmax -> PV -> QK chain.
+      // threshold is the block redone the slow way (scores reloaded from tensor memory - P has not been stored yet -
+      // maximum first, rescale O, exponentiate). Results are identical to always taking the slow path; the maximum
+      // pass leaves the softmax -> PV -> QK chain.
       bool done = false;
       if (FA2_FWD_SPEC && i > 0 && !need_mask) {
-        const float neg_m = -m_ref;  // m_ref == -inf (row without any visible key so far) forces the slow path below
+        const float neg_m = -m_ref;  // m_ref == -inf (row without any visible key so far): x = +inf forces the slow path
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        float xm[8];
+        float xm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xm[e] = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < kBN; j += 2) {
+        for (int j = 0; j < kCols; j += 2) {
           const float x0 = fmaf(s[j], c, neg_m), x1 = fmaf(s[j + 1], c, neg_m);
-          xm[(j / 2) % 8] = fmaxf(xm[(j / 2) % 8], fmaxf(x0, x1));
-          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          xm[(j / 2) % 4] = fmaxf(xm[(j / 2) % 4], fmaxf(x0, x1));
+          float p0, p1;
+          if (FA2_FWD_EMUL_NUM > 0 && ((j / 2) % FA2_FWD_EMUL_DEN) < FA2_FWD_EMUL_NUM) {
+            p0 = ex2_emul(x0);
+            p1 = ex2_emul(x1);
+          } else {
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+          }
           ls[j % 4] += p0;
           ls[j % 4 + 1] += p1;
-          pk[j / 64][(j / 2) % 32] = pack2<kBf16>(p0, p1);
+          pk[j / 2] = pack2<kBf16>(p0, p1);
         }
-        const float xmax = fmaxf(fmaxf(fmaxf(xm[0], xm[1]), fmaxf(xm[2], xm[3])), fmaxf(fmaxf(xm[4], xm[5]), fmaxf(xm[6], xm[7])));
-        const bool redo = !(xmax <= kRescaleThreshold);  // also true for NaN (m_ref == -inf)
+        float xmax = fmaxf(fmaxf(xm[0], xm[1]), fmaxf(xm[2], xm[3]));
+        if constexpr (kHalves == 2) {
+          *xchg_slot(i & 1, half, 1) = xmax;
+          named_bar_sync(1 + t, kTileSmxThreads);
+          xmax = fmaxf(xmax, *xchg_slot(i & 1, half ^ 1, 1));
+        }
+        const bool redo = !(xmax <= kRescaleThreshold);
         if (!__any_sync(0xffffffffu, redo)) {
           l += (ls[0] + ls[2]) + (ls[1] + ls[3]);
           done = true;
+        } else {
+          load_scores();
         }
       }
       if (!done) {
@@ -338,11 +380,18 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[j], s[j + 8]);
 #pragma unroll
-      for (int j = 16; j < kBN; j += 16) {
+      for (int j = 16; j < kCols; j += 16) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], fmaxf(s[j + e], s[j + e + 8]));
       }
-      const float mb = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
+      float mb = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
+      if constexpr (kHalves == 2) {
+        // the two threads of a row must use the same reference maximum: swap block maxima (double buffered by parity:
+        // a slot is rewritten two blocks later, after the barrier of the block in between)
+        *xchg_slot(i & 1, half) = mb;
+        named_bar_sync(1 + t, kTileSmxThreads);
+        mb = fmaxf(mb, *xchg_slot(i & 1, half ^ 1));
+      }
 
       // lazy rescale: only move the reference max when the block max exceeds it by > 2^8
       const bool need = mb > m_ref + kRescaleThreshold;
@@ -352,24 +401,25 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         m_ref = mb;
       }
       if (i > 0 && __any_sync(0xffffffffu, need)) {
-#pragma unroll
-        for (int cidx = 0; cidx < D / 32; ++cidx) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(tO + cidx * 32, o);
+        // rare (the reference maximum moved by more than 2^8): 16 columns at a time keeps the live scores in registers
+#pragma unroll 1
+        for (int cidx = 0; cidx < kOCols / 16; ++cidx) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(tO + cidx * 16, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-          tmem_st_32x32b_x32(tO + cidx * 32, o);
+          for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          tmem_st_32x32b_x16(tO + cidx * 16, o);
         }
       }
       l *= alpha;
 
-      if (r == 0) FA2_STAMP(t, i, 3);
+      if (r == 0 && half == 0) FA2_STAMP(t, i, 3);
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
       auto exp_block = [&](auto emulate) {
 #pragma unroll
-        for (int j = 0; j < kBN; j += 2) {
+        for (int j = 0; j < kCols; j += 2) {
           float pr[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -381,26 +431,32 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             ls[(j + e) % 4] += pr[e];
           }
-          pk[j / 64][(j / 2) % 32] = pack2<kBf16>(pr[0], pr[1]);
+          pk[j / 2] = pack2<kBf16>(pr[0], pr[1]);
         }
       };
       // masked blocks keep every exponential on the MUFU (exact 0 for -inf scores); everywhere else a fixed share
       // is evaluated on the FMA pipes
       if (need_mask) exp_block(std::false_type{}); else exp_block(std::true_type{});
-      const float l0 = ls[0] + ls[2], l1 = ls[1] + ls[3];
-      l += l0 + l1;
+      l += (ls[0] + ls[2]) + (ls[1] + ls[3]);
       }
-      if (r == 0) FA2_STAMP(t, i, 4);
+      if (r == 0 && half == 0) FA2_STAMP(t, i, 4);
 #pragma unroll
-      for (int cidx = 0; cidx < kBN / 64; ++cidx) tmem_st_32x32b_x32(tS + cidx * 32, pk[cidx]);
+      for (int cidx = 0; cidx < kCols / 64; ++cidx) tmem_st_32x32b_x32(tS + cidx * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[cidx * 32]));
       tmem_wait_st();
       tcgen05_fence_before();
       mbar_arrive(&p_full[t]);
-      if (r == 0) FA2_STAMP(t, i, 5);
+      if (r == 0 && half == 0) FA2_STAMP(t, i, 5);
     }
 
     // ------------------------------ epilogue: O / l -> smem -> TMA store ---------------------------
     if (tile_row0 < p.Sq) {
+      if constexpr (kHalves == 2) {
+        // full row sum = the two partial sums (both relative to the same m_ref); slots of parity nblk & 1 are free:
+        // the last block used parity (nblk - 1) & 1 and every thread has passed that block's barrier
+        *xchg_slot(nblk & 1, half) = l;
+        named_bar_sync(1 + t, kTileSmxThreads);
+        l += *xchg_slot(nblk & 1, half ^ 1);
+      }
       const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
       if (nblk > 0) {
         mbar_wait(&o_full[t], 0);
@@ -412,7 +468,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       uint8_t* sO = sQ + t * L::kTileBytes;  // the Q tile is dead once o_full fired
 #pragma unroll
-      for (int cidx = 0; cidx < D / 32; ++cidx) {
+      for (int cidx = 0; cidx < kOCols / 32; ++cidx) {
         uint32_t o[32];
         if (nblk > 0) {
           tmem_ld_32x32b_x32(tO + cidx * 32, o);
@@ -421,7 +477,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = 0u;
         }
-        uint8_t* sub = sO + (cidx / 2) * kSubBytes;
+        const int col = half * kOCols + cidx * 32;  // first head-dim column of this chunk
+        uint8_t* sub = sO + (col / 64) * kSubBytes;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint4 v;
@@ -429,20 +486,20 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
           v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
           v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
-          const uint32_t chunk16 = (cidx % 2) * 4 + q4;
+          const uint32_t chunk16 = ((col % 64) / 8) + q4;
           *reinterpret_cast<uint4*>(sub + sw128_offset(r, chunk16)) = v;
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(1 + t, kBM);
-      if (r == 0) {
+      named_bar_sync(1 + t, kTileSmxThreads);
+      if (r == 0 && half == 0) {
         for (int j = 0; j < kSub; ++j) tma_store_4d(&tmap_o, sO + j * kSubBytes, j * 64, tile_row0, head, batch);
         bulk_commit_group();
         bulk_wait_group_read<0>();
       }
       // LSE (log2 domain), padded rows get 0
       float* lse_row = p.lse + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride;
-      if (row < p.lse_stride) {
+      if (half == 0 && row < p.lse_stride) {
         float lse = 0.f;
         if (row < p.Sq) lse = (l > 0.f) ? m_ref + lg2_approx(l) : -INFINITY;
         lse_row[row] = lse;
@@ -452,7 +509,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc<512>(0u);
   }
