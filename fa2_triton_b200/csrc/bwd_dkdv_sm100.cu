@@ -64,9 +64,14 @@ constexpr int kRegsCmp = kCmpWgs == 4 ? 104 : 208;
 constexpr int kRegsIssue = kCmpWgs == 4 ? 64 : 88;
 constexpr int kQStages = 3;   // Q (+LSE) ring: Q(i) lives from S^T(i) to dK(i), and Q(i+1) is wanted right after dV(i)
 constexpr int kDoStages = 2;  // dO (+delta) ring
+// how many of every 4 pairs of exponentials are evaluated on the FMA pipes (ex2_emul2_neg) instead of the MUFU
 #ifndef FA2_DKDV_EMUL
-#define FA2_DKDV_EMUL 1  // every other pair of exponentials on the FMA pipes (ex2_emul2_neg)
+#define FA2_DKDV_EMUL 2
 #endif
+__host__ __device__ constexpr bool emulate_pair(int q) {
+  return FA2_DKDV_EMUL == 4 ? true : FA2_DKDV_EMUL == 3 ? (q % 4 != 0) : FA2_DKDV_EMUL == 2 ? (q % 2 == 1)
+       : FA2_DKDV_EMUL == 1 ? (q % 4 == 3) : false;
+}
 
 template <int D>
 struct DkdvSmem {
@@ -75,10 +80,14 @@ struct DkdvSmem {
   static constexpr int kVOff = kKOff + kTileBytes;
   static constexpr int kQOff = kVOff + kTileBytes;
   static constexpr int kDOOff = kQOff + kQStages * kTileBytes;
-  static constexpr int kLseOff = kDOOff + kDoStages * kTileBytes;   // kQStages x 512 B (rides with Q)
-  static constexpr int kDeltaOff = kLseOff + kQStages * kBlk * 4;   // kDoStages x 512 B (rides with dO)
+  // The LSE row of query block i rides with Q(i) (stage released by dK(i), i.e. after dS(i)). Its delta row rides with
+  // dO(i), but is read by dS(i) - possibly after dV(i), which releases the dO stage, has retired: the slot has its own
+  // "empty" barrier on which every compute thread arrives once it has its delta values. (Without it the load of block
+  // i + 2 could overwrite the row under a late reader: run-to-run differences at S = 16384.)
+  static constexpr int kLseOff = kDOOff + kDoStages * kTileBytes;   // kQStages x 512 B
+  static constexpr int kDeltaOff = kLseOff + kQStages * kBlk * 4;   // kDoStages x 512 B
   static constexpr int kBarOff = kDeltaOff + kDoStages * kBlk * 4;
-  static constexpr int kNumBars = 16;
+  static constexpr int kNumBars = 18;
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
   static constexpr int kBytes = kTmemSlotOff + 16;
   static_assert(kBytes <= 232448, "dK/dV kernel smem budget exceeded");
@@ -95,6 +104,7 @@ enum DkdvBar {
   kDpFull = 13,
   kDsFull = 14,   // dS^T(i) is in tensor memory (over dP^T)
   kDkvFull = 15,
+  kDeltaEmpty = 16,  // [2] every compute thread has read the delta row in this slot
 };
 
 // streaming 16-byte store (written once, read once by the dQ kernel: evict first)
@@ -163,6 +173,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int s = 0; s < kDoStages; ++s) {
         mbar_init(&bars[kDoFull + s], 1);
         mbar_init(&bars[kDoEmpty + s], 1);
+        mbar_init(&bars[kDeltaEmpty + s], kCmpThreads);
       }
       mbar_init(&bars[kSFull], 1);
       mbar_init(&bars[kPFull], kCmpThreads);
@@ -202,8 +213,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           for (int j = 0; j < kSub; ++j)
             tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, &tmap_q, &bars[kQFull + qs], j * 64, m * kBlk, head, batch);
           bulk_load_1d(sLse + qs * kBlk, p.lse + row_off, kBlk * 4, &bars[kQFull + qs]);
-          // dO(it) + its delta row: released by dV(it - 2)
+          // dO(it) + its delta row: released by dV(it - 2) and by the readers of delta(it - 2)
           mbar_wait(&bars[kDoEmpty + ds], dph ^ 1);
+          mbar_wait(&bars[kDeltaEmpty + ds], dph ^ 1);
           mbar_arrive_expect_tx(&bars[kDoFull + ds], L::kTileBytes + kBlk * 4);
           for (int j = 0; j < kSub; ++j)
             tma_load_4d(sDO + ds * L::kTileBytes + j * kSubBytes, &tmap_do, &bars[kDoFull + ds], j * 64, m * kBlk, head, batch);
@@ -347,8 +359,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const float2 t1 = ffma2(make_float2(__uint_as_float(su[j + 2]), __uint_as_float(su[j + 3])), neg_c2, make_float2(l4.z, l4.w));
         // a fully masked query row carries LSE = -inf: exp2(+inf) = inf here, replaced by 0 in the masked path below
         // (such rows only occur in blocks that need masking)
-        pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
-        if (FA2_DKDV_EMUL) pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
+        if (emulate_pair(j4 * 2)) pf[j4 * 2] = ex2_emul2_neg(t0);
+        else pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
+        if (emulate_pair(j4 * 2 + 1)) pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
         else pf[j4 * 2 + 1] = make_float2(ex2_approx(-t1.x), ex2_approx(-t1.y));
       }
       if (need_mask) {
@@ -400,6 +413,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         w[j4 * 2] = pack2<kBf16>(s0.x, s0.y);
         w[j4 * 2 + 1] = pack2<kBf16>(s1.x, s1.y);
       }
+      mbar_arrive(&bars[kDeltaEmpty + ds]);  // this thread is done with the delta row
       if constexpr (kPairs == 16) tmem_st_32x32b_x16(tDP, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
       else tmem_st_32x32b_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&w[0]));
       tmem_wait_st();

@@ -39,3 +39,9 @@ for n, t in sorted(tot.items(), key=lambda x: -x[1]):
     print(f"  {t / steps:9.1f}  x{cnt[n] / steps:.0f}  {n[:100]}")
     s += t / steps
 print(f"  {s:9.1f}  total")
+# idle time between consecutive kernels of the profiled region (launch gaps the CPU side is responsible for)
+ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+             if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda x: x[0])
+span = (ev[-1][1] - ev[0][0]) / steps
+gaps = sum(max(0.0, b[0] - a[1]) for a, b in zip(ev, ev[1:])) / steps
+print(f"  {span:9.1f}  wall per step (first kernel start to last kernel end), of which {gaps:.1f} us idle between kernels")
