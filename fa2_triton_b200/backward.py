@@ -10,7 +10,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .forward import _reject_out_of_scope, _stream_ptr, encode_dtype
+from .forward import (SUPPORTED_HEAD_DIMS, _reject_out_of_scope, _stream_ptr, encode_dtype, pad_last, padded_head_dim,
+                      sequence_lengths)
 
 # Process-wide default for how dQ contributions are summed.
 #   True     : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
@@ -67,6 +68,32 @@ def _flash_attn_backward(
     (``ctx.needs_input_grad``); the skipped gradients are returned as ``None``."""
     _reject_out_of_scope(attention_mask, bias, dropout_p)
     dO = dO.contiguous() if dO.stride(-1) != 1 else dO
+    if attention_mask is not None:
+        # Variable-length mode (src/backward/caller.py:29-79, 168-176): per-sequence views instead of pack / unpack;
+        # gradients of padded positions are zero.
+        assert q.size(1) == k.size(1), "Attention mask is not supported with seqlen_q != seqlen_k"
+        dq = torch.zeros_like(q, dtype=torch.float32 if dq_dtype is None else dq_dtype) if need_dq else None
+        dk = torch.zeros_like(k) if need_dkdv else None
+        dv = torch.zeros_like(v) if need_dkdv else None
+        for b, n in enumerate(sequence_lengths(attention_mask)):
+            if n == 0:
+                continue
+            n_pad = math.ceil(n / 128) * 128
+            part = _flash_attn_backward(dO[b:b + 1, :n], q[b:b + 1, :n], k[b:b + 1, :n], v[b:b + 1, :n], None, None,
+                                        o[b:b + 1, :n], lse[b:b + 1, :, :n_pad].contiguous(), dropout_p, causal,
+                                        softmax_scale, dropout_seed, deterministic, dq_dtype, need_dq, need_dkdv)
+            for dst, src in zip((dq, dk, dv), part):
+                if dst is not None:
+                    dst[b, :n] = src[0]
+        return dq, dk, dv
+    if q.shape[-1] not in SUPPORTED_HEAD_DIMS:
+        head_dim = q.shape[-1]
+        d = padded_head_dim(head_dim)
+        scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
+        part = _flash_attn_backward(pad_last(dO, d), pad_last(q, d), pad_last(k, d), pad_last(v, d), None, None,
+                                    pad_last(o, d), lse, dropout_p, causal, scale, dropout_seed, deterministic,
+                                    dq_dtype, need_dq, need_dkdv)
+        return tuple(None if t is None else t[..., :head_dim] for t in part)
     batch_size, seqlen_q, nheads_q, head_dim = q.shape
     _, seqlen_k, nheads_kv, _ = k.shape
     max_seqlen_q_rounded = math.ceil(seqlen_q / 128) * 128

@@ -26,10 +26,30 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+SUPPORTED_HEAD_DIMS = (64, 128)
+
+
+def padded_head_dim(head_dim: int) -> int:
+    """The kernels exist for D = 64 and 128; any smaller head dim runs zero-padded to the next of the two (zero
+    columns add nothing to Q K^T and produce zero columns of O, dQ, dK, dV). The reference pads to the next power of
+    two inside its kernels the same way (src/forward/caller.py:77-78, PADDED_HEADS)."""
+    for d in SUPPORTED_HEAD_DIMS:
+        if head_dim <= d:
+            return d
+    raise NotImplementedError(f"head_dim {head_dim}: this build supports head dims up to {SUPPORTED_HEAD_DIMS[-1]}")
+
+
+def pad_last(x: Tensor, d: int) -> Tensor:
+    return x if x.shape[-1] == d else torch.nn.functional.pad(x, (0, d - x.shape[-1]))
+
+
+def sequence_lengths(attention_mask: Tensor):
+    """Per-sequence lengths of a right-padded [B, S] mask (what src/utils.py:14 reads with .item(); one host sync)."""
+    return [int(n) for n in attention_mask.sum(dim=1).tolist()]
+
+
 def _reject_out_of_scope(attention_mask, bias, dropout_p):
-    # varlen masks, additive bias and dropout are outside the hot path of this build.
-    if attention_mask is not None:
-        raise NotImplementedError("attention_mask (varlen packing) is not part of the B200 hot path yet")
+    # SURVEY.md section 8: additive bias and dropout are outside the hot path of this build.
     if bias is not None:
         raise NotImplementedError("attention_bias is not part of the B200 hot path yet")
     if dropout_p and dropout_p > 0:
@@ -46,8 +66,10 @@ def _flash_attn_forward(
     causal: bool = False,
     softmax_scale: Optional[float] = None,
     dropout_seed: Optional[int] = None,
+    out: Optional[Tensor] = None,
 ) -> Tuple[Tensor, Tensor, float, int]:
     """Returns ``(o, lse, softmax_scale, dropout_seed)`` like src/forward/caller.py:122.
+    ``out`` (extension): write O into this tensor (any strides with a contiguous last dimension).
 
     ``lse`` is fp32 ``[B, Hq, ceil(Sq/128)*128]`` in the log2 domain (src/forward/caller.py:73-74,
     src/forward/kernel.py:119); entries past ``Sq`` are 0.
@@ -56,6 +78,33 @@ def _flash_attn_forward(
     batch, seqlen_q, nheads_q, head_dim = q.shape
     _, seqlen_k, nheads_kv, _ = k.shape
     expected_kv_shape = (batch, seqlen_k, nheads_kv, head_dim)
+    if attention_mask is not None:
+        # Variable-length mode (src/forward/caller.py:25-59): every sequence attends within its own unpadded prefix and
+        # padded rows of O are zero. Instead of the reference's pack / unpack copies each sequence is a strided view
+        # handed to the kernel (TMA takes the strides); O is written in place.
+        assert q.size(1) == k.size(1), "Attention mask is not supported with seqlen_q != seqlen_k"
+        assert attention_mask.shape == (batch, seqlen_q), f"{attention_mask.shape = } <> {(batch, seqlen_q) = }"
+        scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
+        o = torch.zeros_like(q)
+        seqlen_q_rounded = math.ceil(seqlen_q / 128) * 128
+        lse = torch.zeros((batch, nheads_q, seqlen_q_rounded), device=q.device, dtype=torch.float32)
+        for b, n in enumerate(sequence_lengths(attention_mask)):
+            if n == 0:
+                continue
+            ob, lb, _, _ = _flash_attn_forward(q[b:b + 1, :n], k[b:b + 1, :n], v[b:b + 1, :n], None, None, 0.0, causal,
+                                               scale, dropout_seed, out=o[b:b + 1, :n])
+            lse[b, :, :lb.shape[-1]] = lb[0]
+        return o, lse, scale, 0 if dropout_seed is None else dropout_seed
+    if head_dim not in SUPPORTED_HEAD_DIMS:
+        d = padded_head_dim(head_dim)
+        scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
+        o, lse, _, seed = _flash_attn_forward(pad_last(q, d), pad_last(k, d), pad_last(v, d), None, None, 0.0, causal,
+                                              scale, dropout_seed)
+        o = o[..., :head_dim]
+        if out is not None:
+            out.copy_(o)
+            o = out
+        return o, lse, scale, seed
     # same checks, same exception type as src/forward/caller.py:36-41
     assert nheads_q % nheads_kv == 0, f"{nheads_q = } is not divisible by {nheads_kv =}"
     assert k.shape == expected_kv_shape, f"{k.shape = } <> {expected_kv_shape = }"
@@ -69,7 +118,8 @@ def _flash_attn_forward(
     lib = _lib.load()
     with torch.cuda.device(q.device):
         # every element of O and of the padded LSE is written by the kernel: no zero fill needed
-        o = torch.empty_like(q)
+        o = torch.empty_like(q) if out is None else out
+        assert o.shape == q.shape and o.dtype == q.dtype and o.stride(-1) == 1
         seqlen_q_rounded = math.ceil(seqlen_q / 128) * 128
         lse = torch.empty((batch, nheads_q, seqlen_q_rounded), device=q.device, dtype=torch.float32)
         code = lib.fa2_sm100_fwd(

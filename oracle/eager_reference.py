@@ -13,8 +13,12 @@ import math
 import torch
 
 
-def flash_attn_reference(q, k, v, causal=False, upcast=True, reorder_ops=False, softmax_scale=None):
+def flash_attn_reference(q, k, v, causal=False, upcast=True, reorder_ops=False, softmax_scale=None, padding_mask=None):
     """q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] -> output [B,Sq,Hq,D] in q's dtype.
+
+    padding_mask: optional bool [B, S] used as both query_padding_mask and key_padding_mask, the way the reference's
+    tests call it (tests/core.py:31-49): padded keys are hidden (:91-92), the causal diagonal follows the per-sequence
+    lengths (:16-29), padded query rows produce zeros (:111-112, :121-122).
 
     upcast: compute in fp32 (src/reference_implementation.py:77-78). reorder_ops: scale K instead of Q
     (:83-86), used by the reference tests to estimate the error of a same-precision implementation.
@@ -33,22 +37,32 @@ def flash_attn_reference(q, k, v, causal=False, upcast=True, reorder_ops=False, 
     else:
         scores = torch.einsum("bthd,bshd->bhts", q * scale, k)
     hidden = None
+    if padding_mask is not None:
+        scores = scores.masked_fill((~padding_mask).unsqueeze(1).unsqueeze(1), float("-inf"))
     if causal:  # :8-29 with window (-1, 0): bottom-right aligned
         row = torch.arange(sq, device=q.device).unsqueeze(-1)
         col = torch.arange(sk, device=q.device)
-        hidden = col > row + (sk - sq)
+        if padding_mask is None:
+            hidden = col > row + (sk - sq)
+        else:  # per-sequence lengths; query and key lengths coincide, so the diagonal is the main one
+            hidden = (col > row).expand(q.shape[0], 1, sq, sk)
         scores = scores.masked_fill(hidden, float("-inf"))
     attn = torch.softmax(scores, dim=-1).to(v.dtype)  # :105
     if hidden is not None:  # rows without any visible key: 0 instead of NaN (:107-108)
         attn = attn.masked_fill(torch.all(hidden, dim=-1, keepdim=True), 0.0)
+    if padding_mask is not None:
+        attn = attn.masked_fill((~padding_mask).unsqueeze(1).unsqueeze(-1), 0.0)
     out = torch.einsum("bhts,bshd->bthd", attn, v)  # :120
+    if padding_mask is not None:
+        out = out.masked_fill((~padding_mask).unsqueeze(-1).unsqueeze(-1), 0.0)
     return out.to(out_dtype)
 
 
-def fwd_bwd(q, k, v, do, causal=False, upcast=True, reorder_ops=False):
+def fwd_bwd(q, k, v, do, causal=False, upcast=True, reorder_ops=False, padding_mask=None, softmax_scale=None):
     """Forward + autograd backward: (out, dq, dk, dv). Inputs are left untouched."""
     q, k, v = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
-    out = flash_attn_reference(q, k, v, causal=causal, upcast=upcast, reorder_ops=reorder_ops)
+    out = flash_attn_reference(q, k, v, causal=causal, upcast=upcast, reorder_ops=reorder_ops, padding_mask=padding_mask,
+                               softmax_scale=softmax_scale)
     dq, dk, dv = torch.autograd.grad(out, (q, k, v), do)
     return out.detach(), dq, dk, dv
 

@@ -75,7 +75,9 @@ def test_python_surface_matches_reference_signatures():
     assert list(inspect.signature(pkg.flash_attn_func).parameters) == want  # src/wrapper.py:89-99
     assert list(inspect.signature(pkg.FlashAttnFunc.forward).parameters) == ["ctx"] + want  # src/wrapper.py:13-24
     fwd = list(inspect.signature(pkg._flash_attn_forward).parameters)
-    assert fwd == ["q", "k", "v", "attention_mask", "bias", "dropout_p", "causal", "softmax_scale", "dropout_seed"]
+    # the reference's nine parameters in its order (src/forward/caller.py:12-22); `out` is a trailing extension
+    assert fwd[:9] == ["q", "k", "v", "attention_mask", "bias", "dropout_p", "causal", "softmax_scale", "dropout_seed"]
+    assert fwd[9:] == ["out"]
     bwd = list(inspect.signature(pkg._flash_attn_backward).parameters)
     assert bwd[:12] == ["dO", "q", "k", "v", "bias", "attention_mask", "o", "lse", "dropout_p", "causal",
                         "softmax_scale", "dropout_seed"]  # src/backward/caller.py:14-27

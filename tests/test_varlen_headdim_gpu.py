@@ -1,0 +1,85 @@
+"""GPU: the "next" rows of SURVEY.md section 8f that live on the host side of the boundary -
+variable-length batches through `attention_mask` (reference tests/core.py with use_attention=True) and head dims
+below 128 that are not 64 / 128 (zero-padded; reference tests/test_fwd_bwd.py:16-35 head_dim grid)."""
+import pytest
+import torch
+
+import fa2_triton_b200 as fa2
+from fa2_test_utils import assert_close_16, assert_reference_criterion, generate_test_data
+from oracle import eager_reference as er
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def right_padded_mask(B, S, seed):
+    """The reference's generate_attention_mask (tests/utils.py:40-56): random right padding, one full sequence."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    pad = torch.randint(0, S - 1, (B,), generator=g).tolist()
+    pad[int(torch.randint(0, B, (1,), generator=g))] = 0
+    m = torch.ones(B, S, dtype=torch.bool)
+    for i, p in enumerate(pad):
+        if p:
+            m[i, -p:] = False
+    return m.to(DEV)
+
+
+def ours(q, k, v, do, causal, mask=None):
+    qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    out = fa2.flash_attn_func(qq, kk, vv, attention_mask=mask, causal=causal)
+    dq, dk, dv = torch.autograd.grad(out, (qq, kk, vv), do)
+    torch.cuda.synchronize()
+    return out.detach(), dq, dk, dv
+
+
+def check(got, q, k, v, do, causal, mask=None):
+    ref = er.fwd_bwd(q, k, v, do, causal=causal, upcast=True, padding_mask=mask)
+    lowp = er.fwd_bwd(q, k, v, do, causal=causal, upcast=False, reorder_ops=True, padding_mask=mask)
+    for name, g, r, lp, mult, atol in (("O", got[0], ref[0], lowp[0], 2, 5e-5), ("dQ", got[1], ref[1], lowp[1], 3, 1e-5),
+                                       ("dK", got[2], ref[2], lowp[2], 3, 1e-5), ("dV", got[3], ref[3], lowp[3], 3, 1e-5)):
+        assert g.shape == r.shape and g.dtype == q.dtype
+        assert_close_16(name, g, r)
+        assert_reference_criterion(name, g, r, lp, mult, atol)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("B,S,Hq,Hkv", [(3, 300, 4, 2), (4, 1024, 2, 2), (2, 113, 3, 3)])
+def test_attention_mask_matches_oracle(B, S, Hq, Hkv, D, causal):
+    q, k, v, do = generate_test_data(B, S, S, Hq, Hkv, D, torch.bfloat16, DEV, seed=B + S)
+    mask = right_padded_mask(B, S, seed=S)
+    got = ours(q, k, v, do, causal, mask)
+    check(got, q, k, v, do, causal, mask)
+    # padded positions: exactly zero outputs and gradients (src/utils.py:26 unpacks into zeros)
+    for t in got:
+        assert (t[~mask] == 0).all()
+
+
+def test_attention_mask_ignores_padded_content():
+    """Whatever sits in the padded rows of q, k, v and dO must not reach any result."""
+    B, S, H, D = 3, 384, 2, 128
+    q, k, v, do = generate_test_data(B, S, S, H, H, D, torch.bfloat16, DEV, seed=9)
+    mask = right_padded_mask(B, S, seed=4)
+    a = ours(q, k, v, do, True, mask)
+    q2, k2, v2, do2 = (t.clone() for t in (q, k, v, do))
+    for t, val in ((q2, 31.0), (k2, -17.0), (v2, 55.0), (do2, 3.0)):
+        t[~mask] = val
+    b = ours(q2, k2, v2, do2, True, mask)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [16, 32, 40, 96, 111])
+def test_padded_head_dims_match_oracle(D, causal):
+    B, Sq, Sk, Hq, Hkv = 2, 200, 328, 4, 2
+    q, k, v, do = generate_test_data(B, Sq, Sk, Hq, Hkv, D, torch.bfloat16, DEV, seed=D)
+    if D % 8:  # odd head dims come out of generate_test_data contiguous: fine, padding makes the copies the kernels see
+        assert q.stride(-1) == 1
+    check(ours(q, k, v, do, causal), q, k, v, do, causal)
+
+
+def test_head_dim_above_128_is_rejected():
+    q, k, v, _ = generate_test_data(1, 128, 128, 2, 2, 256, torch.bfloat16, DEV)
+    with pytest.raises(NotImplementedError):
+        fa2.flash_attn_func(q, k, v)
