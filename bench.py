@@ -371,7 +371,7 @@ def main():
         e2e = {"value": flops_global / tt.item() / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": plan.h2d_bytes,
                "d2h_bytes_per_step": plan.d2h_bytes, "ms_per_step": tt.item() * 1e3, "steps": n_e2e,
                "api": "fa2_triton_b200.host_api.HostAttention (pinned host q,k,v,dO in; o,dq,dk,dv out; "
-                      f"{plan.chunks} batch chunks over 3 streams)"}
+                      f"{plan.chunks} (batch, head range) chunks over 3 streams, pitched copies)"}
 
     # -------------------------------------------- CPU baseline (rank 0, N=1) --------------------------------------
     cpu = None

@@ -311,6 +311,17 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
   return 0;
 }
 
+int fa2_sm100_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                           size_t rows, int to_device, void* stream) {
+  if (!dst || !src) return fail(FA2_E_NULL_POINTER, "copy2d: null pointer");
+  if (width_bytes > dst_pitch || width_bytes > src_pitch) return fail(FA2_E_BAD_SHAPE, "copy2d: row wider than its pitch");
+  cudaError_t ce = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows,
+                                     to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                     static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_copy2d_async");
+  return 0;
+}
+
 #ifdef FA2_TRACE
 int fa2_sm100_debug_fetch_trace(int which, long long* host, size_t n) {
   switch (which) {

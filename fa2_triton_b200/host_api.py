@@ -1,9 +1,13 @@
 """Host-buffer entry point: attention forward + backward for tensors that live in (pinned) host memory.
 
 This is what a caller that keeps activations off-device binds to, and what ``bench.py`` times as ``e2e``: every
-call moves q, k, v, dO host->device, runs the four kernels, and moves O, dQ, dK, dV device->host. The batch is cut
-into chunks that flow through three streams (upload / compute / download), so the PCIe transfers of neighbouring
-chunks overlap each other (the link is full duplex) and the kernels.
+call moves q, k, v, dO host->device, runs the four kernels, and moves O, dQ, dK, dV device->host. The work is cut
+into (batch element, kv-head range) chunks - independent units of attention - that flow
+through three streams (upload / compute / download), so the PCIe transfers of neighbouring chunks overlap each other
+(the link is full duplex) and the kernels. A chunk is a pitched slice of the [B, S, H, D] host tensors: it is moved
+with cudaMemcpy2DAsync (fa2_sm100_copy2d_async) straight between the caller's pinned buffers and the device tensors,
+never packed. The link bounds the call (config 3: 512 MiB each way), so what matters is the pipeline fill - the upload
+of the first chunk and the download of the last - hence ~16 chunks rather than one per batch element.
 """
 from __future__ import annotations
 
@@ -12,8 +16,20 @@ from typing import Dict, Optional, Tuple
 import torch
 from torch import Tensor
 
+from . import _lib
 from .backward import _flash_attn_backward
 from .forward import _flash_attn_forward
+
+
+def _copy_slice(dst: Tensor, src: Tensor, to_device: bool, stream: torch.cuda.Stream) -> None:
+    """dst / src: equally shaped [S, h, D] slices (rows of h * D contiguous elements, any row pitch)."""
+    assert dst.shape == src.shape and dst.stride(-1) == 1 and src.stride(-1) == 1
+    assert dst.stride(1) == dst.shape[2] and src.stride(1) == src.shape[2]
+    es = dst.element_size()
+    code = _lib.load().fa2_sm100_copy2d_async(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es,
+                                              dst.shape[1] * dst.shape[2] * es, dst.shape[0], int(to_device),
+                                              stream.cuda_stream)
+    _lib.check(code, "fa2_sm100_copy2d_async")
 
 
 class HostAttention:
@@ -22,9 +38,16 @@ class HostAttention:
     def __init__(self, q_shape, kv_shape, dtype=torch.bfloat16, device="cuda:0", chunks: Optional[int] = None):
         assert torch.cuda.is_available(), "HostAttention needs a CUDA device; there is no CPU fallback"
         self.device = torch.device(device)
-        B = q_shape[0]
-        self.chunks = min(B, chunks) if chunks else B
-        self.bounds = [(i * B // self.chunks, (i + 1) * B // self.chunks) for i in range(self.chunks)]
+        B, Hq, Hkv = q_shape[0], q_shape[2], kv_shape[2]
+        self.group = Hq // Hkv
+        want = chunks if chunks else 16
+        per_batch = max(1, min(Hkv, want // B))
+        while Hkv % per_batch:  # equal kv-head ranges
+            per_batch -= 1
+        step = Hkv // per_batch
+        # (batch element, first kv head, last kv head + 1)
+        self.units = [(b, g, g + step) for b in range(B) for g in range(0, Hkv, step)]
+        self.chunks = len(self.units)
         dev = dict(device=self.device, dtype=dtype)
         self.d: Dict[str, Tensor] = {
             "q": torch.empty(q_shape, **dev), "k": torch.empty(kv_shape, **dev), "v": torch.empty(kv_shape, **dev),
@@ -47,28 +70,33 @@ class HostAttention:
         """q, k, v, do: host tensors (pinned for asynchronous copies). Returns pinned host (o, dq, dk, dv); they
         are valid when the call returns (it synchronises on the download stream)."""
         src = {"q": q, "k": k, "v": v, "do": do}
+        for name, t in src.items():
+            assert t.shape == self.d[name].shape and t.dtype == self.d[name].dtype and t.is_contiguous(), name
         caller = torch.cuda.current_stream(self.device)
         self.s_in.wait_stream(caller)
         keep = []
-        for (b0, b1) in self.bounds:
-            with torch.cuda.stream(self.s_in):
-                for name in ("q", "k", "v", "do"):
-                    self.d[name][b0:b1].copy_(src[name][b0:b1], non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(self.s_in)
+        grp = self.group
+        for (b, g0, g1) in self.units:
+            heads = {"q": (g0 * grp, g1 * grp), "do": (g0 * grp, g1 * grp), "k": (g0, g1), "v": (g0, g1),
+                     "o": (g0 * grp, g1 * grp), "dq": (g0 * grp, g1 * grp), "dk": (g0, g1), "dv": (g0, g1)}
+            for name in ("q", "k", "v", "do"):
+                h0, h1 = heads[name]
+                _copy_slice(self.d[name][b, :, h0:h1], src[name][b, :, h0:h1], True, self.s_in)
+            ready = torch.cuda.Event()
+            ready.record(self.s_in)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(ready)
-                qc, kc, vc, doc = (self.d[n][b0:b1] for n in ("q", "k", "v", "do"))
+                qc, kc, vc, doc = (self.d[n][b:b + 1, :, heads[n][0]:heads[n][1]] for n in ("q", "k", "v", "do"))
                 o, lse, scale, _ = _flash_attn_forward(qc, kc, vc, None, None, 0.0, causal, softmax_scale, None)
                 dq, dk, dv = _flash_attn_backward(doc, qc, kc, vc, None, None, o, lse, 0.0, causal, scale, None,
                                                   deterministic=deterministic, dq_dtype=qc.dtype)
                 done = torch.cuda.Event()
                 done.record(self.s_run)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(done)
-                for name, t in (("o", o), ("dq", dq), ("dk", dk), ("dv", dv)):
-                    self.h[name][b0:b1].copy_(t, non_blocking=True)
-                    t.record_stream(self.s_out)
+            self.s_out.wait_event(done)
+            for name, t in (("o", o), ("dq", dq), ("dk", dk), ("dv", dv)):
+                h0, h1 = heads[name]
+                _copy_slice(self.h[name][b, :, h0:h1], t[0], False, self.s_out)
+                t.record_stream(self.s_out)
             keep.append((o, dq, dk, dv, lse))
         caller.wait_stream(self.s_out)
         self.s_out.synchronize()

@@ -112,6 +112,12 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq,
                          int B, int Hq, int Sq, int D,
                          const int64_t dq_strides[3], float softmax_scale, int out_dtype, void* stream);
 
+/* Pitched asynchronous copy between (pinned) host memory and the device on `stream`: `rows` rows of `width_bytes`,
+ * `to_device` != 0: host -> device, else device -> host. This is how a host-buffer caller moves one (batch, head range)
+ * slice of a [B, S, H, D] tensor without packing it first (fa2_triton_b200/host_api.py; bench.py's `e2e`). */
+int fa2_sm100_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                           size_t rows, int to_device, void* stream);
+
 /* Hardware probe used by the test-suite: D[128, N] = A * B through one UMMA operand path.
  * a_mode 0: A [128, K] row-major (smem, K-major)   1: A given transposed [K, 128] (smem, MN-major)
  *        2: A [128, K] row-major staged in tensor memory
