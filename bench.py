@@ -298,7 +298,10 @@ def main():
                                      S_pad, scale, int(causal), mode, 17, 17, stream), "bwd")
 
     def time_call(fn, pre=None):
-        tot = 0.0
+        # back-to-back launches, one event pair per launch on the launching stream, a single synchronize at the end:
+        # the GPU never idles between launches (with a host sync after every launch the next kernel starts from a
+        # dropped clock state and times 20-30 % slower than inside a step)
+        evs = []
         for i in range(n_rep + 2):
             if pre is not None:
                 pre()
@@ -306,10 +309,9 @@ def main():
             a.record()
             fn()
             b.record()
-            torch.cuda.synchronize()
-            if i >= 2:
-                tot += a.elapsed_time(b)
-        return tot / n_rep
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs[2:]) / n_rep
 
     f_fwd = fa_flops(B_local, H, S, S, D, causal, False)
     kern = {"fa2_fwd_kernel": {"ms": time_call(call_fwd), "algorithmic_flop": f_fwd}}

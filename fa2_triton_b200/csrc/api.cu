@@ -155,9 +155,8 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
 
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int causal, int deterministic) {
   if (B < 1 || Hq < 1 || Sq < 1 || D < 1) return 0;
-  if (deterministic == FA2_DQ_NONE) return 0;
-  if (deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_ONLY)
-    return 256;  // dQ is produced by its own kernel: no accumulator, only the work-item counter of its scheduler
+  if (deterministic == FA2_DQ_NONE || deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_ONLY)
+    return 256;  // no accumulator, only the work-item counters of the persistent kernels' schedulers
   if (deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ) {
     // scheduler counter (padded to 1 KB) + one 32 KB dS tile per visible (query block, key block) pair
     if (Sk < 1) return 0;
@@ -227,9 +226,18 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   const bool spill = deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ;
   const long long tiles_per_head = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);
   void* spill_base = spill ? static_cast<char*>(workspace) + 1024 : nullptr;
+  if (!fused) {
+    // work-item counters of the persistent kernels (they re-zero them themselves; this covers the first use of the
+    // buffer): dQ kernel at byte 0, dK/dV kernel at byte 64
+    ce = cudaMemsetAsync(workspace, 0, 128, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd scheduler counter memset");
+  }
   if (want_dkdv) {
-    // FA2_SM100_OLD_DKDV=1 (A/B switch): the unfused instantiation of the fused kernel, P^T kept in tensor memory
+    // A/B switches: FA2_SM100_OLD_DKDV=1 the unfused instantiation of the fused kernel (P^T in tensor memory, dS^T in
+    // shared memory); FA2_SM100_DKDV_PERSISTENT=1 the persistent dK/dV kernel instead of one CTA per key block
+    // (measured 1.04 ms against 1.03: under the power cap hiding the per-CTA prologue buys nothing)
     static const bool old_dkdv = [] { const char* e = getenv("FA2_SM100_OLD_DKDV"); return e && e[0] == '1'; }();
+    static const bool nonpersistent = [] { const char* e = getenv("FA2_SM100_DKDV_PERSISTENT"); return !(e && e[0] == '1'); }();
     if (fused || (old_dkdv && !spill)) {
       ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
     } else {
@@ -242,7 +250,11 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
       k.softmax_scale = softmax_scale;
       k.scale_log2 = softmax_scale * kLog2e;
       k.causal = causal ? 1 : 0;
-      ce = fa2::launch_bwd_dkdv(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
+      k.sched = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
+      k.dk = dk; k.dv = dv;
+      for (int i = 0; i < 3; ++i) { k.dk_strides[i] = dk_strides[i]; k.dv_strides[i] = dv_strides[i]; }
+      if (nonpersistent) ce = fa2::launch_bwd_dkdv(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
+      else ce = fa2::launch_bwd_dkdv_persistent(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
   }
@@ -252,9 +264,6 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
     // dQ accumulator -> caller's tensor
     return fa2_sm100_dq_convert(workspace, dq, B, Hq, Sq, D, dq_strides, softmax_scale, dq_dtype, stream);
   }
-  // work-item counter of the persistent dQ kernel (it re-zeroes it itself; this covers the first use of the buffer)
-  ce = cudaMemsetAsync(workspace, 0, 16, st);
-  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd scheduler counter memset");
   if (spill) {
     fa2::DqSpillParams d{};
     d.ds_spill = spill_base;

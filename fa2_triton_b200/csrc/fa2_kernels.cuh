@@ -112,7 +112,17 @@ struct DkdvParams {
   float softmax_scale;
   float scale_log2;
   int causal;
+  // persistent variant only: work-item counter (0 on entry, re-zeroed by the kernel) and the output tensors, which it
+  // writes straight from registers
+  int* sched;
+  void* dk;
+  void* dv;
+  int64_t dk_strides[3];  // batch, head, seq (elements)
+  int64_t dv_strides[3];
 };
+cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
+                                       const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,
+                                       cudaStream_t stream);
 cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                             const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk,
                             const CUtensorMap& tdv, const DkdvParams& p, cudaStream_t stream);

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 6
+#define FA2_SM100_ABI_VERSION 7
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -85,9 +85,9 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
                         int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Bytes of scratch fa2_sm100_bwd needs. FA2_DQ_ATOMIC / FA2_DQ_FUSED_ORDERED: the fp32 dQ accumulator plus one int per
- * (batch, head, 128-row query tile). FA2_DQ_DETERMINISTIC / FA2_DQ_ONLY: 256 bytes (work-item counter of the
- * persistent dQ kernel; cleared by the call itself). FA2_DQ_DET_SPILL (and 6, 7): 1 KB + B * Hq * (visible block pairs) * 32 KB
- * (`causal` decides which pairs are visible; B=4, H=32, S=4096 causal: 2.06 GiB). FA2_DQ_NONE: 0.
+ * (batch, head, 128-row query tile). FA2_DQ_DETERMINISTIC / FA2_DQ_ONLY / FA2_DQ_NONE: 256 bytes (work-item counters of
+ * the persistent kernels; cleared by the call itself). FA2_DQ_DET_SPILL (and 6, 7): 1 KB + B * Hq * (visible block pairs) * 32 KB
+ * (`causal` decides which pairs are visible; B=4, H=32, S=4096 causal: 2.06 GiB).
  * The workspace must be 16-byte aligned. */
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int causal, int deterministic);
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/fa2_sm100.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.fa2_sm100_version() == 6
+    assert lib.fa2_sm100_version() == 7
 
 
 def test_workspace_size_formula():
@@ -43,7 +43,7 @@ def test_workspace_size_formula():
     # deterministic / dQ only: dQ has its own kernel, nothing to accumulate into - just its scheduler's counter
     assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 1) == 256
     assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 4) == 256
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 3) == 0
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 3) == 256
     # deterministic with spilled dS: 1 KB + one 32 KB tile per visible 128 x 128 block pair
     assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 5) == 1024 + 4 * 32 * (32 * 33 // 2) * 32768
     assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 0, 5) == 1024 + 4 * 32 * 32 * 32 * 32768
