@@ -321,7 +321,10 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const float2 neg_c2 = make_float2(-p.scale_log2, -p.scale_log2);
     // spill: this thread's 16-byte pieces of dS^T(m, n) go to [piece = 8 queries][key row][16 B] inside the 32 KB tile,
     // so that one warp store covers 512 contiguous bytes. (A dedicated spill warpgroup reading dS^T back from tensor
-    // memory was slower: 1.09 ms against 1.02 - four warps do not keep the 32 B/clk/SM store path busy.)
+    // memory was slower: 1.09 ms against 1.02 - four warps do not keep the 32 B/clk/SM store path busy. Replacing the
+    // closed-form tile address below - a division and a 64-bit product per thread and iteration, ~15 % of the kernel's
+    // instructions - by incremental pointers was slower as well: 1.08 ms against 1.04, the stores then pile up
+    // earlier. With the chip at its power cap and the store path ~45 % busy, fewer instructions are not faster.)
     uint8_t* spill_row = nullptr;
     long long prefix = 0;
     // The store path takes ~32 B/clk/SM: the 32 KB of a block pair occupy it for >= 1000 cycles, and a warp that issues
@@ -977,7 +980,8 @@ static cudaError_t launch_bwd_dkdv_persistent_t(const CUtensorMap& tq, const CUt
     configured[dev] = true;
   }
   const int n_items = ((p.Sk + kBlk - 1) / kBlk) * p.Hkv * p.B;
-  const int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas;
   dim3 grid(n_items < sms ? n_items : sms);
   kernel<<<grid, kThreads, smem, stream>>>(tq, tk, tv, tdo, p);
   return cudaGetLastError();

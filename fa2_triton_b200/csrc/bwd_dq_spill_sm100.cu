@@ -255,7 +255,8 @@ static cudaError_t launch_bwd_dq_spill_t(const CUtensorMap& tk, const DqSpillPar
     configured[dev] = true;
   }
   const int n_items = ((p.Sq + kBlk - 1) / kBlk) * p.Hq * p.B;
-  const int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas;
   dim3 grid(n_items < sms ? n_items : sms);  // persistent: one CTA per SM
   kernel<<<grid, kThreads, smem, stream>>>(tk, p);
   return cudaGetLastError();

@@ -119,6 +119,7 @@ struct DkdvParams {
   void* dv;
   int64_t dk_strides[3];  // batch, head, seq (elements)
   int64_t dv_strides[3];
+  int max_ctas;           // > 0: cap on the persistent grid (the rest of the SMs is left to a concurrent kernel)
 };
 cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                                        const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,
@@ -138,6 +139,7 @@ struct DqSpillParams {
   int B, Hq, Hkv, Sq, Sk;
   float softmax_scale;
   int causal;
+  int max_ctas;        // > 0: cap on the persistent grid
 };
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream);
 
