@@ -19,7 +19,9 @@ from .forward import (SUPPORTED_HEAD_DIMS, _reject_out_of_scope, _stream_ptr, en
 #              kernel spills its 16-bit dS tiles to a workspace (32 KB per visible 128 x 128 block pair) and the dQ
 #              kernel only sums dS K over them: 5 matrix products per block pair (mode 5). If that workspace does
 #              not fit (FA2_SPILL_MAX_GIB, default 72, or an allocation failure) the dQ kernel recomputes S, P, dP and
-#              dS like the reference (7 products, 256 bytes of workspace; mode 1).
+#              dS like the reference (7 products, 256 bytes of workspace; mode 1). Head dim 64 always recomputes: a
+#              dS tile is 32 KB whatever the head dim while the products it saves are half as large, and measured
+#              (B=2, H=16, S=16384, D=64 non-causal, 20 launches back to back) recomputing takes 8.34 ms against 9.07.
 #   1 / 5    : force the recomputing / the spilling deterministic path.
 #   False / 0: atomic fast mode - the dK/dV kernel also forms dQ partial products and adds them into an fp32
 #              accumulator in arrival order (5 products per block pair).
@@ -109,7 +111,7 @@ def _flash_attn_backward(
     det = _DETERMINISTIC if deterministic is None else deterministic
     auto = isinstance(det, bool) and det  # True: spill when the workspace fits, else recompute
     if isinstance(det, bool):
-        mode = _lib.DQ_DET_SPILL if det else _lib.DQ_ATOMIC
+        mode = (_lib.DQ_DET_SPILL if q.shape[-1] > 64 else _lib.DQ_DETERMINISTIC) if det else _lib.DQ_ATOMIC
     else:
         mode = int(det) if det in (0, 1, 2, 5) else int(bool(det))  # one of _lib.DQ_*
     if not need_dq and not need_dkdv:

@@ -57,6 +57,15 @@ constexpr int kRegsIssue = kCmpWgs == 4 ? 64 : 88;
 constexpr int kKStages = 3;
 constexpr int kVStages = 2;
 constexpr int kSchedSlots = 4;
+// how many of every 4 pairs of exponentials are evaluated on the FMA pipes (ex2_emul2) instead of the MUFU: at D = 64 the
+// three products of a block pair take 768 tensor-pipe cycles, its 16384 exponentials 1024 MUFU cycles
+#ifndef FA2_DQ_EMUL
+#define FA2_DQ_EMUL 1  // measured, dQ kernel alone: D = 64, S = 16384: 0/4 -> 3.45 ms, 1/4 -> 3.30, 2/4 -> 3.39; D = 128, S = 4096: 0/4 -> 0.786, 2/4 -> 0.748
+#endif
+__host__ __device__ constexpr bool dq_emulate_pair(int q) {
+  return FA2_DQ_EMUL == 4 ? true : FA2_DQ_EMUL == 3 ? (q % 4 != 0) : FA2_DQ_EMUL == 2 ? (q % 2 == 1)
+       : FA2_DQ_EMUL == 1 ? (q % 4 == 3) : false;
+}
 
 template <int D>
 struct DqSmem {
@@ -364,7 +373,8 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
         for (int j = 0; j < kPairs; ++j) {
           const float2 x = ffma2(make_float2(__uint_as_float(su[2 * j]), __uint_as_float(su[2 * j + 1])), c2, nl2);
-          pf[j] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          if (dq_emulate_pair(j)) pf[j] = ex2_emul2(x);
+          else pf[j] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
         }
         if (need_mask) {
           const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
