@@ -66,10 +66,17 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between
 // 1/3 -> 0.616, 1/2 -> 0.651: with one softmax warp per scheduler the phase is latency-bound, not MUFU-bound, and the
 // extra dependent instructions cost more than the MUFU slots they free. Default: off.
 #ifndef FA2_FWD_EMUL_NUM
-#define FA2_FWD_EMUL_NUM 0
+#define FA2_FWD_EMUL_NUM (D == 64 ? 1 : 0)  // evaluated inside the kernel template
 #endif
 #ifndef FA2_FWD_EMUL_DEN
 #define FA2_FWD_EMUL_DEN 4
+#endif
+// Packed flavour (whole pairs through ex2_emul2, f32x2 arithmetic). Measured, same box and call: D = 64 (S = 16384,
+// non-causal, where the 16384 exponentials of a tile take twice as long on the MUFU as its two products on the tensor
+// pipe): 1 of 4 pairs 3.15 -> 2.92 ms, 2 of 4 3.21; D = 128 (S = 4096 causal): 0.560 -> 0.566 / 0.561. Hence the
+// default: a quarter of the pairs at D = 64, none at D = 128.
+#ifndef FA2_FWD_EMUL_PACKED
+#define FA2_FWD_EMUL_PACKED 1
 #endif
 // Speculative exponentials against the previous reference maximum (see the softmax loop). Off: no gain (see above).
 #ifndef FA2_FWD_SPEC
@@ -421,6 +428,20 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
         for (int j = 0; j < kCols; j += 2) {
           float pr[2];
+#if FA2_FWD_EMUL_PACKED
+          // whole pairs on the FMA pipes with the f32x2 flavour (half the issue slots of the scalar one)
+          if (decltype(emulate)::value && ((j / 2) % FA2_FWD_EMUL_DEN) < FA2_FWD_EMUL_NUM) {
+            const float2 x2 = ffma2(make_float2(s[j], s[j + 1]), make_float2(c, c), make_float2(neg_m, neg_m));
+            const float2 p2 = ex2_emul2(x2);
+            pr[0] = p2.x;
+            pr[1] = p2.y;
+          } else {
+            pr[0] = ex2_approx(fmaf(s[j], c, neg_m));
+            pr[1] = ex2_approx(fmaf(s[j + 1], c, neg_m));
+          }
+          ls[j % 4] += pr[0];
+          ls[j % 4 + 1] += pr[1];
+#else
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const float x = fmaf(s[j + e], c, neg_m);
@@ -431,6 +452,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             ls[(j + e) % 4] += pr[e];
           }
+#endif
           pk[j / 2] = pack2<kBf16>(pr[0], pr[1]);
         }
       };
