@@ -106,46 +106,56 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
   constexpr int kThreadsPerRow = D / 8;
-  constexpr int kRowsPerBlock = 256 / kThreadsPerRow;
+  constexpr int kRowsPerPass = 256 / kThreadsPerRow;
+  constexpr int kPasses = 4;  // rows per thread: all 2 x kPasses 16-byte loads are issued before the first use
+  constexpr int kRowsPerBlock = kRowsPerPass * kPasses;
   const int head = blockIdx.y, batch = blockIdx.z;
-  const int row = blockIdx.x * kRowsPerBlock + threadIdx.x / kThreadsPerRow;
+  const int row0 = blockIdx.x * kRowsPerBlock + threadIdx.x / kThreadsPerRow;
   const int part = threadIdx.x % kThreadsPerRow;
-  float acc = 0.f;
-  if (row < p.Sq) {
-    const uint16_t* o = reinterpret_cast<const uint16_t*>(p.o) + batch * p.o_strides[0] + head * p.o_strides[1] +
-                        static_cast<int64_t>(row) * p.o_strides[2] + part * 8;
-    const uint16_t* g = reinterpret_cast<const uint16_t*>(p.dout) + batch * p.do_strides[0] + head * p.do_strides[1] +
-                        static_cast<int64_t>(row) * p.do_strides[2] + part * 8;
-    const uint4 ov = *reinterpret_cast<const uint4*>(o);
-    const uint4 gv = *reinterpret_cast<const uint4*>(g);
-    const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
-    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+  const uint16_t* obase = reinterpret_cast<const uint16_t*>(p.o) + batch * p.o_strides[0] + head * p.o_strides[1] + part * 8;
+  const uint16_t* gbase = reinterpret_cast<const uint16_t*>(p.dout) + batch * p.do_strides[0] + head * p.do_strides[1] + part * 8;
+  uint4 ov[kPasses], gv[kPasses];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kPasses; ++i) {
+    const int row = row0 + i * kRowsPerPass;
+    ov[i] = gv[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (row < p.Sq) {
+      ov[i] = *reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(row) * p.o_strides[2]);
+      gv[i] = *reinterpret_cast<const uint4*>(gbase + static_cast<int64_t>(row) * p.do_strides[2]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPasses; ++i) {
+    const int row = row0 + i * kRowsPerPass;
+    const uint32_t ow[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
+    const uint32_t gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       float2 a, b;
       if constexpr (kBf16) {
-        a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[i]));
-        b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
+        a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[j]));
+        b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[j]));
       } else {
-        a = __half22float2(*reinterpret_cast<const __half2*>(&ow[i]));
-        b = __half22float2(*reinterpret_cast<const __half2*>(&gw[i]));
+        a = __half22float2(*reinterpret_cast<const __half2*>(&ow[j]));
+        b = __half22float2(*reinterpret_cast<const __half2*>(&gw[j]));
       }
       acc = fmaf(a.x, b.x, acc);
       acc = fmaf(a.y, b.y, acc);
     }
-  }
 #pragma unroll
-  for (int off = kThreadsPerRow / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (part == 0 && row < p.lse_stride)
-    p.delta[(static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + row] = acc;  // padded rows: 0
+    for (int off = kThreadsPerRow / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (part == 0 && row < p.lse_stride)
+      p.delta[(static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + row] = acc;  // padded rows: 0
+  }
   // Clear this CTA's share of the backward workspace (fp32 dQ accumulator + ordered-reduction tickets), so the
-  // fused kernel that follows on the stream needs no separate memset: kRowsPerBlock * D floats = 2 float4 / thread.
+  // fused kernel that follows on the stream needs no separate memset: kRowsPerBlock * D floats.
   if (p.dq_accum != nullptr) {
     const int64_t bh = static_cast<int64_t>(batch) * p.Hq + head;
+    const int rows_here = min(kRowsPerBlock, p.lse_stride - static_cast<int>(blockIdx.x) * kRowsPerBlock);
     float4* dst = reinterpret_cast<float4*>(p.dq_accum + (bh * p.lse_stride + static_cast<int64_t>(blockIdx.x) * kRowsPerBlock) * D);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    dst[threadIdx.x] = z;
-    dst[threadIdx.x + 256] = z;
+    for (int i = threadIdx.x; i < rows_here * D / 4; i += 256) dst[i] = z;
     if (blockIdx.x == 0 && p.dq_sem != nullptr) {
       const int tiles = p.lse_stride / 128;
       for (int i = threadIdx.x; i < tiles; i += 256) p.dq_sem[bh * tiles + i] = 0;
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
 }
 
 cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream) {
-  const int rows_per_block = 256 / (p.D / 8);
+  const int rows_per_block = 4 * (256 / (p.D / 8));
   dim3 grid((p.lse_stride + rows_per_block - 1) / rows_per_block, p.Hq, p.B);
   if (p.D == 128) {
     if (bf16) fa2_delta_kernel<128, true><<<grid, 256, 0, stream>>>(p);
