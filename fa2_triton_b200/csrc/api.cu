@@ -252,7 +252,8 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
       k.causal = causal ? 1 : 0;
       k.sched = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
       k.dk = dk; k.dv = dv;
-      if (const char* e = getenv("FA2_SM100_DKDV_CTAS")) k.max_ctas = atoi(e);
+      static const int dkdv_ctas = [] { const char* e = getenv("FA2_SM100_DKDV_CTAS"); return e ? atoi(e) : 0; }();
+      k.max_ctas = dkdv_ctas;  // experiments only (scripts/concurrent_probe.py): cap on the persistent grid
       for (int i = 0; i < 3; ++i) { k.dk_strides[i] = dk_strides[i]; k.dv_strides[i] = dv_strides[i]; }
       if (nonpersistent) ce = fa2::launch_bwd_dkdv(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
       else ce = fa2::launch_bwd_dkdv_persistent(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
@@ -276,7 +277,8 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
     d.B = B; d.Hq = Hq; d.Hkv = Hkv; d.Sq = Sq; d.Sk = Sk;
     d.softmax_scale = softmax_scale;
     d.causal = causal ? 1 : 0;
-    if (const char* e = getenv("FA2_SM100_DQ_CTAS")) d.max_ctas = atoi(e);
+    static const int dq_ctas = [] { const char* e = getenv("FA2_SM100_DQ_CTAS"); return e ? atoi(e) : 0; }();
+    d.max_ctas = dq_ctas;  // experiments only: cap on the persistent grid
     ce = fa2::launch_bwd_dq_spill(D, dtype == FA2_DTYPE_BF16, tk, d, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ (spill) launch");
     return 0;
