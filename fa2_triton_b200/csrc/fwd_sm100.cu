@@ -75,6 +75,15 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between
 // non-causal, where the 16384 exponentials of a tile take twice as long on the MUFU as its two products on the tensor
 // pipe): 1 of 4 pairs 3.15 -> 2.92 ms, 2 of 4 3.21; D = 128 (S = 4096 causal): 0.560 -> 0.566 / 0.561. Hence the
 // default: a quarter of the pairs at D = 64, none at D = 128.
+// Energy / time ablations for DESIGN.md (results are WRONG on purpose, never shipped): 1 = exponentials replaced by a
+// move, 2 = additionally no maximum pass / rescale, 3 = no softmax arithmetic at all (P = rounded raw scores, no row sum)
+#ifndef FA2_FWD_ABLATE
+#define FA2_FWD_ABLATE 0
+#endif
+// Experiment: both exponentials of a pair in one MUFU.EX2.F16x2 (the arguments and results pass through fp16)
+#ifndef FA2_FWD_EX2_F16
+#define FA2_FWD_EX2_F16 0
+#endif
 #ifndef FA2_FWD_EMUL_PACKED
 #define FA2_FWD_EMUL_PACKED 1
 #endif
@@ -383,6 +392,14 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
       }
       if (!done) {
+#if FA2_FWD_ABLATE >= 3
+      {
+#pragma unroll
+        for (int j = 0; j < kCols; j += 2) pk[j / 2] = pack2<kBf16>(s[j], s[j + 1]);
+        l = 1.f; m_ref = 0.f; done = true;
+      }
+      if (!done) {
+#endif
       float mx[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[j], s[j + 8]);
@@ -392,6 +409,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], fmaxf(s[j + e], s[j + e + 8]));
       }
       float mb = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
+#if FA2_FWD_ABLATE == 2
+      mb = s[0] * c;
+#endif
       if constexpr (kHalves == 2) {
         // the two threads of a row must use the same reference maximum: swap block maxima (double buffered by parity:
         // a slot is rewritten two blocks later, after the barrier of the block in between)
@@ -436,8 +456,22 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             pr[0] = p2.x;
             pr[1] = p2.y;
           } else {
+#if FA2_FWD_ABLATE >= 1
+            pr[0] = fmaf(s[j], c, neg_m);
+            pr[1] = fmaf(s[j + 1], c, neg_m);
+#elif FA2_FWD_EX2_F16
+            {
+              uint32_t xh, ph;
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(fmaf(s[j + 1], c, neg_m)), "f"(fmaf(s[j], c, neg_m)));
+              asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(xh));
+              const float2 pf2 = __half22float2(*reinterpret_cast<const __half2*>(&ph));
+              pr[0] = pf2.x;
+              pr[1] = pf2.y;
+            }
+#else
             pr[0] = ex2_approx(fmaf(s[j], c, neg_m));
             pr[1] = ex2_approx(fmaf(s[j + 1], c, neg_m));
+#endif
           }
           ls[j % 4] += pr[0];
           ls[j % 4 + 1] += pr[1];
@@ -461,6 +495,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (need_mask) exp_block(std::false_type{}); else exp_block(std::true_type{});
       l += (ls[0] + ls[2]) + (ls[1] + ls[3]);
       }
+#if FA2_FWD_ABLATE >= 3
+      }
+#endif
       if (r == 0 && half == 0) FA2_STAMP(t, i, 4);
 #pragma unroll
       for (int cidx = 0; cidx < kCols / 64; ++cidx) tmem_st_32x32b_x32(tS + cidx * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[cidx * 32]));
