@@ -41,11 +41,17 @@ SIGNATURES = {
     "fa2_sm100_last_error": (ctypes.c_char_p, []),
     "fa2_sm100_fwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 4
                       + [_c_int64, _c_float, _c_int, _c_int, _c_void_p]),
+    "fa2_sm100_fwd_ext": (_c_int, [_c_void_p] * 5 + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 4
+                          + [_c_int64, _c_float, _c_int, _c_int]
+                          + [_c_void_p, _c_int, ctypes.POINTER(_c_int64), _c_float, ctypes.c_uint64, _c_void_p]),
     "fa2_sm100_bwd_delta": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)] * 2
                             + [_c_int64, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "fa2_sm100_bwd_workspace_bytes": (_c_size_t, [_c_int] * 7),
     "fa2_sm100_bwd": (_c_int, [_c_void_p] * 10 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 7
                       + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "fa2_sm100_bwd_ext": (_c_int, [_c_void_p] * 10 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 7
+                          + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_int]
+                          + [_c_void_p, _c_int, ctypes.POINTER(_c_int64), _c_void_p]),
     "fa2_sm100_dq_convert": (_c_int, [_c_void_p] * 2 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)]
                              + [_c_float, _c_int, _c_void_p]),
     "fa2_sm100_copy2d_async": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_size_t, _c_size_t, _c_size_t, _c_int, _c_void_p]),
@@ -85,6 +91,18 @@ def strides3(t):
     """(batch, head, seq) element strides of a [B, S, H, D] tensor - the triple the reference passes to its
     kernels as ``x.stride(0), x.stride(2), x.stride(1)`` (src/forward/caller.py:93-96)."""
     return _I64x3(t.stride(0), t.stride(2), t.stride(1))
+
+
+def bias_args(bias):
+    """(pointer, dtype code, (batch, head, row) element strides) of an attention bias [1 | B, 1 | Hq, Sq, Sk]; size-1
+    dimensions broadcast with stride 0 (what src/utils.py:57-77 computes). ``None`` -> (None, 0, None)."""
+    if bias is None:
+        return None, 0, None
+    import torch
+    code = {torch.float16: DTYPE_FP16, torch.bfloat16: DTYPE_BF16, torch.float32: DTYPE_FP32}[bias.dtype]
+    sb = bias.stride(0) if bias.size(0) > 1 else 0
+    sh = bias.stride(1) if bias.size(1) > 1 else 0
+    return bias.data_ptr(), code, _I64x3(sb, sh, bias.stride(2))
 
 
 def check(code: int, what: str):

@@ -10,8 +10,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .forward import (SUPPORTED_HEAD_DIMS, _reject_out_of_scope, _stream_ptr, encode_dtype, pad_last, padded_head_dim,
-                      sequence_lengths)
+from .forward import (SUPPORTED_HEAD_DIMS, _stream_ptr, check_bias, encode_dtype, handle_dropout, pad_last,
+                      padded_head_dim, sequence_lengths)
 
 # Process-wide default for how dQ contributions are summed.
 #   True     : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
@@ -68,9 +68,10 @@ def _flash_attn_backward(
     dtype - the rounding autograd would apply to the reference's fp32 dq anyway - and saves one pass over dq.
     ``need_dq`` / ``need_dkdv`` (extension): skip the kernel whose outputs autograd does not ask for
     (``ctx.needs_input_grad``); the skipped gradients are returned as ``None``."""
-    _reject_out_of_scope(attention_mask, bias, dropout_p)
+    handle_dropout(dropout_p, dropout_seed, is_forward=False)  # raises NotImplementedError under dropout, like src/utils.py:87-88
     dO = dO.contiguous() if dO.stride(-1) != 1 else dO
     if attention_mask is not None:
+        assert bias is None, "Attention mask is not supported along with attention bias. Just use bias instead."
         # Variable-length mode (src/backward/caller.py:29-79, 168-176): per-sequence views instead of pack / unpack;
         # gradients of padded positions are zero.
         assert q.size(1) == k.size(1), "Attention mask is not supported with seqlen_q != seqlen_k"
@@ -92,7 +93,7 @@ def _flash_attn_backward(
         head_dim = q.shape[-1]
         d = padded_head_dim(head_dim)
         scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
-        part = _flash_attn_backward(pad_last(dO, d), pad_last(q, d), pad_last(k, d), pad_last(v, d), None, None,
+        part = _flash_attn_backward(pad_last(dO, d), pad_last(q, d), pad_last(k, d), pad_last(v, d), bias, None,
                                     pad_last(o, d), lse, dropout_p, causal, scale, dropout_seed, deterministic,
                                     dq_dtype, need_dq, need_dkdv)
         return tuple(None if t is None else t[..., :head_dim] for t in part)
@@ -108,7 +109,10 @@ def _flash_attn_backward(
     assert q.is_cuda and k.is_cuda and v.is_cuda and o.is_cuda and dO.is_cuda and lse.is_cuda
     assert q.dtype == k.dtype == v.dtype == o.dtype == dO.dtype, "All tensors must have the same type"
     assert lse.dtype == torch.float32 and lse.is_contiguous()
+    bias = check_bias(bias, q, batch_size, nheads_q, seqlen_q, seqlen_k)
     det = _DETERMINISTIC if deterministic is None else deterministic
+    if bias is not None and det in (False, 0, 2):
+        det = True  # the fused (atomic / ticket-ordered) kernel has no bias variant: the deterministic kernels serve it
     auto = isinstance(det, bool) and det  # True: spill when the workspace fits, else recompute
     if isinstance(det, bool):
         mode = (_lib.DQ_DET_SPILL if q.shape[-1] > 64 else _lib.DQ_DETERMINISTIC) if det else _lib.DQ_ATOMIC
@@ -154,13 +158,13 @@ def _flash_attn_backward(
             _lib.strides3(o), _lib.strides3(dO), max_seqlen_q_rounded, dt,
             ws_ptr if fused else None, ws_bytes if fused else 0, stream)
         _lib.check(code, "fa2_sm100_bwd_delta")
-        code = lib.fa2_sm100_bwd(
+        code = lib.fa2_sm100_bwd_ext(
             dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(), delta.data_ptr(),
             ptr(dq), ptr(dk), ptr(dv), ws_ptr, ws_bytes,
             batch_size, nheads_q, nheads_kv, seqlen_q, seqlen_k, head_dim,
             _lib.strides3(dO), _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
             s3(dq, q), s3(dk, k), s3(dv, v),
             max_seqlen_q_rounded, softmax_scale, int(bool(causal)), mode, dt,
-            encode_dtype(dq) if dq is not None else dt, stream)
+            encode_dtype(dq) if dq is not None else dt, *_lib.bias_args(bias), stream)
         _lib.check(code, "fa2_sm100_bwd")
     return dq, dk, dv

@@ -86,6 +86,25 @@ int check_common(int B, int Hq, int Hkv, int Sq, int Sk, int D, int dtype) {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// bias: [1 | B, 1 | Hq, Sq, Sk] with (batch, head, row) element strides; a broadcast dimension carries stride 0
+int make_bias_view(fa2::BiasView* view, const void* bias, int bias_dtype, const int64_t bias_strides[3], int dtype) {
+  *view = fa2::BiasView{};
+  if (!bias) return 0;
+  if (bias_dtype != dtype && bias_dtype != FA2_DTYPE_FP32)
+    return fail(FA2_E_UNSUPPORTED_DTYPE, "bias dtype code %d: must be the input dtype (%d) or 32 (fp32)", bias_dtype, dtype);
+  if (!bias_strides) return fail(FA2_E_NULL_POINTER, "bias_strides: null pointer");
+  const int elem = bias_dtype == FA2_DTYPE_FP32 ? 4 : 2;
+  if (reinterpret_cast<uintptr_t>(bias) % elem) return fail(FA2_E_BAD_ALIGNMENT, "bias: base not element aligned");
+  for (int i = 0; i < 3; ++i)
+    if (bias_strides[i] < 0) return fail(FA2_E_BAD_SHAPE, "bias: negative stride");
+  view->ptr = bias;
+  view->is_fp32 = bias_dtype == FA2_DTYPE_FP32 ? 1 : 0;
+  view->sb = bias_strides[0];
+  view->sh = bias_strides[1];
+  view->sm = bias_strides[2];
+  return 0;
+}
+
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
@@ -100,7 +119,17 @@ int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
                   const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
                   void* stream) {
+  return fa2_sm100_fwd_ext(q, k, v, o, lse, B, Hq, Hkv, Sq, Sk, D, q_strides, k_strides, v_strides, o_strides,
+                           lse_row_stride, softmax_scale, causal, dtype, nullptr, 0, nullptr, 0.f, 0ull, stream);
+}
+
+int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int Sq,
+                      int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                      const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
+                      const void* bias, int bias_dtype, const int64_t bias_strides[3], float dropout_p,
+                      uint64_t dropout_seed, void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
+  if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(FA2_E_BAD_SHAPE, "dropout_p must be in [0, 1)");
   if (!lse) return fail(FA2_E_NULL_POINTER, "lse: null pointer");
   if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
   if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
@@ -116,6 +145,12 @@ int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* l
   p.scale_log2 = softmax_scale * kLog2e;
   p.causal = causal ? 1 : 0;
   p.n_pairs = (Sq + 255) / 256;
+  if (int e = make_bias_view(&p.bias, bias, bias_dtype, bias_strides, dtype)) return e;
+  p.bias_mul = 1.0f / softmax_scale;
+  p.dropout_p = dropout_p;
+  p.inv_keep = 1.0f / (1.0f - dropout_p);
+  p.seed_lo = static_cast<uint32_t>(dropout_seed & 0xffffffffull);
+  p.seed_hi = static_cast<uint32_t>(dropout_seed >> 32);
   cudaError_t ce = fa2::launch_fwd(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, to, p, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_fwd launch");
   return 0;
@@ -175,7 +210,25 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
                   const int64_t k_strides[3], const int64_t v_strides[3], const int64_t dq_strides[3],
                   const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride, float softmax_scale,
                   int causal, int deterministic, int dtype, int dq_dtype, void* stream) {
+  return fa2_sm100_bwd_ext(dout, q, k, v, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, Hq, Hkv, Sq, Sk, D,
+                           do_strides, q_strides, k_strides, v_strides, dq_strides, dk_strides, dv_strides,
+                           lse_row_stride, softmax_scale, causal, deterministic, dtype, dq_dtype, nullptr, 0, nullptr,
+                           stream);
+}
+
+int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void* v, const float* lse,
+                      const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+                      int Hq, int Hkv, int Sq, int Sk, int D, const int64_t do_strides[3], const int64_t q_strides[3],
+                      const int64_t k_strides[3], const int64_t v_strides[3], const int64_t dq_strides[3],
+                      const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride,
+                      float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype, const void* bias,
+                      int bias_dtype, const int64_t bias_strides[3], void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
+  fa2::BiasView bias_view{};
+  if (int e = make_bias_view(&bias_view, bias, bias_dtype, bias_strides, dtype)) return e;
+  if (bias && (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED))
+    return fail(FA2_E_BAD_SHAPE, "bias: the fused (atomic / ticket-ordered) backward has no bias variant; use a "
+                                 "deterministic mode (1, 3, 4, 5, 6)");
   const bool want_dq = deterministic != FA2_DQ_NONE && deterministic != FA2_DQ_SPILL_DKDV;
   const bool want_dkdv = deterministic != FA2_DQ_ONLY && deterministic != FA2_DQ_SPILL_DQ;
   if (!lse || !delta) return fail(FA2_E_NULL_POINTER, "lse / delta: null pointer");
@@ -238,7 +291,7 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
     // (measured 1.04 ms against 1.03: under the power cap hiding the per-CTA prologue buys nothing)
     static const bool old_dkdv = [] { const char* e = getenv("FA2_SM100_OLD_DKDV"); return e && e[0] == '1'; }();
     static const bool nonpersistent = [] { const char* e = getenv("FA2_SM100_DKDV_PERSISTENT"); return !(e && e[0] == '1'); }();
-    if (fused || (old_dkdv && !spill)) {
+    if (fused || (old_dkdv && !spill && !bias)) {
       ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
     } else {
       fa2::DkdvParams k{};
@@ -255,7 +308,8 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
       static const int dkdv_ctas = [] { const char* e = getenv("FA2_SM100_DKDV_CTAS"); return e ? atoi(e) : 0; }();
       k.max_ctas = dkdv_ctas;  // experiments only (scripts/concurrent_probe.py): cap on the persistent grid
       for (int i = 0; i < 3; ++i) { k.dk_strides[i] = dk_strides[i]; k.dv_strides[i] = dv_strides[i]; }
-      if (nonpersistent) ce = fa2::launch_bwd_dkdv(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
+      k.bias = bias_view;
+      if (nonpersistent || bias) ce = fa2::launch_bwd_dkdv(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
       else ce = fa2::launch_bwd_dkdv_persistent(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
@@ -296,6 +350,7 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
   d.softmax_scale = softmax_scale;
   d.scale_log2 = softmax_scale * kLog2e;
   d.causal = causal ? 1 : 0;
+  d.bias = bias_view;
   ce = fa2::launch_bwd_dq(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, tdq, d, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ launch");
   return 0;

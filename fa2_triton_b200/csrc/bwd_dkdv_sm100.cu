@@ -118,7 +118,8 @@ __device__ __forceinline__ void st_global_cs_v4(void* p, uint32_t a, uint32_t b,
 
 }  // namespace
 
-template <int D, bool kBf16, bool kSpill>
+// kBias: the variant that adds the attention bias to the recomputed scores (extras.cuh)
+template <int D, bool kBf16, bool kSpill, bool kBias>
 __global__ void __launch_bounds__(kThreads, 1)
 fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -346,6 +347,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float4* lse_s = reinterpret_cast<const float4*>(sLse + qs * kBlk + wg * kCmpCols);
       const float4* delta_s = reinterpret_cast<const float4*>(sDelta + ds * kBlk + wg * kCmpCols);
       const bool need_mask = (kv0 + kBlk > p.Sk) || (m * kBlk + kBlk > p.Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
+      int64_t bias_head_off = 0;
+      if constexpr (kBias) bias_head_off = batch * p.bias.sb + (head_kv * group + it / m_count) * p.bias.sh;
+      (void)bias_head_off;
 
       // ---- P^T = exp2(S^T * c - LSE) = exp2(-(LSE - S^T * c)) ----
       if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 0);
@@ -366,10 +370,27 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const float2 t1 = ffma2(make_float2(__uint_as_float(su[j + 2]), __uint_as_float(su[j + 3])), neg_c2, make_float2(l4.z, l4.w));
         // a fully masked query row carries LSE = -inf: exp2(+inf) = inf here, replaced by 0 in the masked path below
         // (such rows only occur in blocks that need masking)
+        if constexpr (kBias) {
+          // P = exp2(S c + bias log2(e) - LSE) (src/backward/compute_dkdv.py:60-69). All on the MUFU: a bias of -inf
+          // (used as a mask) must give exactly 0, and a row hidden entirely that way carries LSE = -inf
+          float tt[4] = {t0.x, t0.y, t1.x, t1.y};
+          const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int qi = q0 + j + e;
+            float b = 0.f;
+            if (qi < p.Sq && kv < p.Sk) b = bias_load<kBf16>(p.bias, bias_head_off + static_cast<int64_t>(qi) * p.bias.sm + kv);
+            tt[e] = fmaf(b, -1.4426950408889634f, tt[e]);
+            tt[e] = (ll[e] == -INFINITY) ? INFINITY : tt[e];
+          }
+          pf[j4 * 2] = make_float2(ex2_approx(-tt[0]), ex2_approx(-tt[1]));
+          pf[j4 * 2 + 1] = make_float2(ex2_approx(-tt[2]), ex2_approx(-tt[3]));
+        } else {
         if (emulate_pair(j4 * 2)) pf[j4 * 2] = ex2_emul2_neg(t0);
         else pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
         if (emulate_pair(j4 * 2 + 1)) pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
         else pf[j4 * 2 + 1] = make_float2(ex2_approx(-t1.x), ex2_approx(-t1.y));
+        }
       }
       if (need_mask) {
 #pragma unroll
@@ -998,11 +1019,11 @@ cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUten
   return cudaErrorInvalidValue;
 }
 
-template <int D, bool kBf16, bool kSpill>
+template <int D, bool kBf16, bool kSpill, bool kBias>
 static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                      const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
                                      const DkdvParams& p, cudaStream_t stream) {
-  auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill>;
+  auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kBias>;
   constexpr int smem = DkdvSmem<D>::kBytes;
   static bool configured[64] = {};
   int dev = 0;
@@ -1020,8 +1041,11 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
 cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                             const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk,
                             const CUtensorMap& tdv, const DkdvParams& p, cudaStream_t stream) {
-#define FA2_DKDV_CASE(DD, BF, SP) \
-  if (D == DD && bf16 == BF && spill == SP) return launch_bwd_dkdv_t<DD, BF, SP>(tq, tk, tv, tdo, tdk, tdv, p, stream);
+  const bool has_bias = p.bias.ptr != nullptr;
+#define FA2_DKDV_CASE(DD, BF, SP)                                                                                     \
+  if (D == DD && bf16 == BF && spill == SP)                                                                           \
+    return has_bias ? launch_bwd_dkdv_t<DD, BF, SP, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)                       \
+                    : launch_bwd_dkdv_t<DD, BF, SP, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
   FA2_DKDV_CASE(128, true, true) FA2_DKDV_CASE(128, true, false) FA2_DKDV_CASE(128, false, true) FA2_DKDV_CASE(128, false, false)
   FA2_DKDV_CASE(64, true, true) FA2_DKDV_CASE(64, true, false) FA2_DKDV_CASE(64, false, true) FA2_DKDV_CASE(64, false, false)
 #undef FA2_DKDV_CASE

@@ -109,7 +109,8 @@ __device__ __forceinline__ DqItem dq_item(int w, int n_q_blocks, int Hq) {
 
 }  // namespace
 
-template <int D, bool kBf16>
+// kBias: the variant that adds the attention bias to the recomputed scores (extras.cuh)
+template <int D, bool kBf16, bool kBias>
 __global__ void __launch_bounds__(kDqThreads, 1)
 fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                   const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -373,8 +374,23 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
         for (int j = 0; j < kPairs; ++j) {
           const float2 x = ffma2(make_float2(__uint_as_float(su[2 * j]), __uint_as_float(su[2 * j + 1])), c2, nl2);
+          if constexpr (kBias) {
+            // P = exp2(S c + bias log2(e) - LSE) (src/backward/compute_dq.py:40-51); on the MUFU so that a bias of
+            // -inf gives exactly 0; a row hidden entirely that way (LSE = -inf) gets P = 0
+            float xx[2] = {x.x, x.y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = col0 + 2 * j + e;
+              float b = 0.f;
+              if (row < p.Sq && col < p.Sk)
+                b = bias_load<kBf16>(p.bias, it.batch * p.bias.sb + it.head * p.bias.sh + static_cast<int64_t>(row) * p.bias.sm + col);
+              xx[e] = (nlse == INFINITY) ? -INFINITY : fmaf(b, 1.4426950408889634f, xx[e]);
+            }
+            pf[j] = make_float2(ex2_approx(xx[0]), ex2_approx(xx[1]));
+          } else {
           if (dq_emulate_pair(j)) pf[j] = ex2_emul2(x);
           else pf[j] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          }
         }
         if (need_mask) {
           const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
@@ -473,11 +489,11 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
 }
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kBias>
 static cudaError_t launch_bwd_dq_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                    const CUtensorMap& tdo, const CUtensorMap& tdq, const DqParams& p,
                                    cudaStream_t stream) {
-  auto kernel = fa2_bwd_dq_kernel<D, kBf16>;
+  auto kernel = fa2_bwd_dq_kernel<D, kBf16, kBias>;
   constexpr int smem = DqSmem<D>::kBytes;
   static bool configured[64] = {};
   static int sm_count[64] = {};
@@ -499,10 +515,13 @@ static cudaError_t launch_bwd_dq_t(const CUtensorMap& tq, const CUtensorMap& tk,
 
 cudaError_t launch_bwd_dq(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           const CUtensorMap& tdo, const CUtensorMap& tdq, const DqParams& p, cudaStream_t stream) {
-  if (D == 128) return bf16 ? launch_bwd_dq_t<128, true>(tq, tk, tv, tdo, tdq, p, stream)
-                            : launch_bwd_dq_t<128, false>(tq, tk, tv, tdo, tdq, p, stream);
-  if (D == 64) return bf16 ? launch_bwd_dq_t<64, true>(tq, tk, tv, tdo, tdq, p, stream)
-                           : launch_bwd_dq_t<64, false>(tq, tk, tv, tdo, tdq, p, stream);
+  const bool has_bias = p.bias.ptr != nullptr;
+#define FA2_DQ_CASE(DD, BF)                                                                     \
+  if (D == DD && bf16 == BF)                                                                    \
+    return has_bias ? launch_bwd_dq_t<DD, BF, true>(tq, tk, tv, tdo, tdq, p, stream)            \
+                    : launch_bwd_dq_t<DD, BF, false>(tq, tk, tv, tdo, tdq, p, stream);
+  FA2_DQ_CASE(128, true) FA2_DQ_CASE(128, false) FA2_DQ_CASE(64, true) FA2_DQ_CASE(64, false)
+#undef FA2_DQ_CASE
   return cudaErrorInvalidValue;
 }
 

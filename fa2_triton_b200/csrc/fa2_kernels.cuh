@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "extras.cuh"
+
 namespace fa2 {
 
 // ---------------------------------------------------------------------------------------------
@@ -17,6 +19,12 @@ struct FwdParams {
   float scale_log2;  // softmax_scale * log2(e)
   int causal;
   int n_pairs;       // ceil(Sq / 256): one CTA per pair of 128-row query tiles
+  // extras (kernel variant kExt; all zero otherwise)
+  BiasView bias;
+  float bias_mul;       // 1 / softmax_scale: the bias joins the raw scores, which are multiplied by scale_log2 later
+  float dropout_p;      // 0: no dropout
+  float inv_keep;       // 1 / (1 - dropout_p)
+  uint32_t seed_lo, seed_hi;
 };
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -70,6 +78,7 @@ struct DqParams {
   float softmax_scale;
   float scale_log2;
   int causal;
+  BiasView bias;       // kernel variant kBias; ptr == nullptr otherwise
 };
 cudaError_t launch_bwd_dq(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           const CUtensorMap& tdo, const CUtensorMap& tdq, const DqParams& p, cudaStream_t stream);
@@ -120,6 +129,7 @@ struct DkdvParams {
   int64_t dk_strides[3];  // batch, head, seq (elements)
   int64_t dv_strides[3];
   int max_ctas;           // > 0: cap on the persistent grid (the rest of the SMs is left to a concurrent kernel)
+  BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
 };
 cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                                        const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,

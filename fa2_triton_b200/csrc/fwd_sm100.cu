@@ -119,7 +119,8 @@ __device__ __forceinline__ int num_kv_blocks(int row0, int Sq, int Sk, int causa
 
 }  // namespace
 
-template <int D, bool kBf16>
+// kExt: the variant with additive bias and / or dropout (runtime: p.bias.ptr, p.dropout_p), see extras.cuh
+template <int D, bool kBf16, bool kExt>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -321,6 +322,12 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
     float m_ref = -INFINITY;
     float l = 0.f;  // kHalves == 2: the sum over this thread's columns only
+    // linear index of this row's first score in a [B, Hq, Sq, Sk] tensor, modulo 2^32: the dropout counter
+    // (src/forward/kernel.py:147-149)
+    const uint32_t drop_row_off =
+        ((static_cast<uint32_t>(batch) * p.Hq + head) * static_cast<uint32_t>(p.Sq) + static_cast<uint32_t>(row)) *
+        static_cast<uint32_t>(p.Sk);
+    (void)drop_row_off;
 
     for (int i = 0; i < nblk; ++i) {
       if (r == 0 && half == 0) FA2_STAMP(t, i, 0);
@@ -347,6 +354,32 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
 #pragma unroll
         for (int j = 0; j < kCols; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
+      }
+
+      if constexpr (kExt) {
+        // additive bias (src/forward/compute_row_blocks.py:48-54, 68-69): joins the raw scores as bias / softmax_scale,
+        // so that the common factor c = softmax_scale * log2(e) applies to both; hidden entries stay at -inf
+        if (p.bias.ptr != nullptr && row < p.Sq) {
+          const int64_t off = batch * p.bias.sb + head * p.bias.sh + static_cast<int64_t>(row) * p.bias.sm + col0;
+          const int n_valid = p.Sk - col0;  // columns of this block that exist
+          const uint16_t* b16 = static_cast<const uint16_t*>(p.bias.ptr) + off;
+          if (!p.bias.is_fp32 && n_valid >= kCols && (reinterpret_cast<uintptr_t>(b16) & 15u) == 0) {
+#pragma unroll
+            for (int j = 0; j < kCols; j += 8) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(b16 + j));
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                s[j + 2 * e] = fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] & 0xffffu)), p.bias_mul, s[j + 2 * e]);
+                s[j + 2 * e + 1] = fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] >> 16)), p.bias_mul, s[j + 2 * e + 1]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kCols; ++j)
+              if (j < n_valid) s[j] = fmaf(bias_load<kBf16>(p.bias, off + j), p.bias_mul, s[j]);
+          }
+        }
       }
 
       uint32_t pk[kCols / 2];
@@ -475,6 +508,14 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           ls[j % 4] += pr[0];
           ls[j % 4 + 1] += pr[1];
+          if constexpr (kExt) {
+            // dropout hits P after its row sum was taken (src/forward/compute_row_blocks.py:73-79)
+            if (p.dropout_p > 0.f) {
+              const uint32_t off = drop_row_off + static_cast<uint32_t>(col0 + j);
+              pr[0] = dropout_keep(p.seed_lo, p.seed_hi, off, p.dropout_p) ? pr[0] : 0.f;
+              pr[1] = dropout_keep(p.seed_lo, p.seed_hi, off + 1u, p.dropout_p) ? pr[1] : 0.f;
+            }
+          }
 #else
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -516,7 +557,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         named_bar_sync(1 + t, kTileSmxThreads);
         l += *xchg_slot(nblk & 1, half ^ 1);
       }
-      const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+      float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+      if constexpr (kExt) {
+        if (p.dropout_p > 0.f) inv_l *= p.inv_keep;  // src/forward/kernel.py:256-257
+      }
       if (nblk > 0) {
         mbar_wait(&o_full[t], 0);
         tcgen05_fence_after();
@@ -577,10 +621,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kExt>
 static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                 const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
-  auto kernel = fa2_fwd_kernel<D, kBf16>;
+  auto kernel = fa2_fwd_kernel<D, kBf16, kExt>;
   constexpr int smem = FwdSmem<D>::kDynBytes;
   static bool configured[64] = {};
   int dev = 0;
@@ -603,10 +647,11 @@ cudaError_t fetch_fwd_trace(long long* host, size_t n) {
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
-  if (D == 128) return bf16 ? launch_fwd_t<128, true>(tq, tk, tv, to, p, stream)
-                            : launch_fwd_t<128, false>(tq, tk, tv, to, p, stream);
-  if (D == 64) return bf16 ? launch_fwd_t<64, true>(tq, tk, tv, to, p, stream)
-                           : launch_fwd_t<64, false>(tq, tk, tv, to, p, stream);
+  const bool ext = p.bias.ptr != nullptr || p.dropout_p > 0.f;
+#define FA2_FWD_CASE(d, b, e) if (D == d && bf16 == b && ext == e) return launch_fwd_t<d, b, e>(tq, tk, tv, to, p, stream);
+  FA2_FWD_CASE(128, true, false) FA2_FWD_CASE(128, false, false) FA2_FWD_CASE(64, true, false) FA2_FWD_CASE(64, false, false)
+  FA2_FWD_CASE(128, true, true) FA2_FWD_CASE(128, false, true) FA2_FWD_CASE(64, true, true) FA2_FWD_CASE(64, false, true)
+#undef FA2_FWD_CASE
   return cudaErrorInvalidValue;
 }
 

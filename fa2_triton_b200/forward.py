@@ -48,12 +48,37 @@ def sequence_lengths(attention_mask: Tensor):
     return [int(n) for n in attention_mask.sum(dim=1).tolist()]
 
 
-def _reject_out_of_scope(attention_mask, bias, dropout_p):
-    # additive bias and dropout are outside the hot path of this build.
-    if bias is not None:
-        raise NotImplementedError("attention_bias is not part of the B200 hot path yet")
-    if dropout_p and dropout_p > 0:
-        raise NotImplementedError("dropout is not part of the B200 hot path yet")
+def check_bias(bias: Optional[Tensor], q: Tensor, batch: int, nheads_q: int, seqlen_q: int, seqlen_k: int):
+    """Validate an attention bias ``[1 | B, 1 | Hq, Sq, Sk]`` and return it with a contiguous last dimension.
+
+    Same acceptance rule and exception types as the reference's ``infer_bias_strides`` (src/utils.py:57-77) - with the
+    head dimension compared against the head COUNT (the reference compares a stride, :70, which rejects per-head
+    biases unless the stride happens to equal the count). The bias is indexed by the query head in both passes
+    (the reference's forward uses the kv head, src/forward/kernel.py:141, its backward the query head,
+    src/backward/kernel.py:143; they coincide for its own tests, which use a ``[1, 1, Sq, Sk]`` bias)."""
+    if bias is None:
+        return None
+    assert bias.is_cuda
+    assert bias.dim() == 4 and (bias.size(2) == seqlen_q and bias.size(3) == seqlen_k), f"{bias.shape = }"
+    if bias.size(0) not in (1, batch):
+        raise ValueError(f"Attention bias has {bias.size(0) = } while {batch = }")
+    if bias.size(1) not in (1, nheads_q):
+        raise ValueError(f"Attention bias has {bias.size(1) = } while {nheads_q = }")
+    if bias.dtype not in (q.dtype, torch.float32):
+        raise ValueError(f"Attention bias has dtype {bias.dtype}: expected {q.dtype} or torch.float32")
+    return bias if bias.stride(-1) == 1 else bias.contiguous()
+
+
+def handle_dropout(dropout_p: float, dropout_seed: Optional[int], is_forward: bool) -> int:
+    """The reference's rule (src/utils.py:80-88): no dropout -> seed 0; forward draws a seed when none is given; the
+    backward pass has no dropout."""
+    assert dropout_p >= 0, f"Dropout probability {dropout_p = } must be above 0."
+    assert dropout_p < 1, f"Dropout probability {dropout_p = } must be strictly below 1."
+    if dropout_p == 0:
+        return 0
+    if is_forward:
+        return torch.randint(low=0, high=2**32, size=(1,)).item() if dropout_seed is None else dropout_seed
+    raise NotImplementedError("Backward pass does not yet support dropout.")
 
 
 def _flash_attn_forward(
@@ -74,11 +99,15 @@ def _flash_attn_forward(
     ``lse`` is fp32 ``[B, Hq, ceil(Sq/128)*128]`` in the log2 domain (src/forward/caller.py:73-74,
     src/forward/kernel.py:119); entries past ``Sq`` are 0.
     """
-    _reject_out_of_scope(attention_mask, bias, dropout_p)
     batch, seqlen_q, nheads_q, head_dim = q.shape
     _, seqlen_k, nheads_kv, _ = k.shape
     expected_kv_shape = (batch, seqlen_k, nheads_kv, head_dim)
     if attention_mask is not None:
+        assert bias is None, "Attention mask is not supported along with attention bias. Just use bias instead."
+        if dropout_p and dropout_p > 0:
+            # the reference numbers its dropout counters over the packed batch (src/forward/kernel.py:147-149); the
+            # per-sequence views used here would draw a different mask
+            raise NotImplementedError("dropout together with attention_mask is not supported")
         # Variable-length mode (src/forward/caller.py:25-59): every sequence attends within its own unpadded prefix and
         # padded rows of O are zero. Instead of the reference's pack / unpack copies each sequence is a strided view
         # handed to the kernel (TMA takes the strides); O is written in place.
@@ -98,8 +127,8 @@ def _flash_attn_forward(
     if head_dim not in SUPPORTED_HEAD_DIMS:
         d = padded_head_dim(head_dim)
         scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
-        o, lse, _, seed = _flash_attn_forward(pad_last(q, d), pad_last(k, d), pad_last(v, d), None, None, 0.0, causal,
-                                              scale, dropout_seed)
+        o, lse, _, seed = _flash_attn_forward(pad_last(q, d), pad_last(k, d), pad_last(v, d), None, bias, dropout_p,
+                                              causal, scale, dropout_seed)
         o = o[..., :head_dim]
         if out is not None:
             out.copy_(o)
@@ -113,7 +142,9 @@ def _flash_attn_forward(
     assert q.dtype in [torch.float16, torch.bfloat16], "Only support fp16 and bf16"
     assert q.is_cuda and k.is_cuda and v.is_cuda
     softmax_scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
-    dropout_seed = 0 if dropout_seed is None else dropout_seed
+    # bias and dropout (src/forward/caller.py:66-67)
+    bias = check_bias(bias, q, batch, nheads_q, seqlen_q, seqlen_k)
+    dropout_seed = handle_dropout(dropout_p, dropout_seed, is_forward=True)
 
     lib = _lib.load()
     with torch.cuda.device(q.device):
@@ -122,10 +153,14 @@ def _flash_attn_forward(
         assert o.shape == q.shape and o.dtype == q.dtype and o.stride(-1) == 1
         seqlen_q_rounded = math.ceil(seqlen_q / 128) * 128
         lse = torch.empty((batch, nheads_q, seqlen_q_rounded), device=q.device, dtype=torch.float32)
-        code = lib.fa2_sm100_fwd(
-            q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
-            batch, nheads_q, nheads_kv, seqlen_q, seqlen_k, head_dim,
-            _lib.strides3(q), _lib.strides3(k), _lib.strides3(v), _lib.strides3(o),
-            seqlen_q_rounded, softmax_scale, int(bool(causal)), encode_dtype(q), _stream_ptr(q.device))
+        args = (q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                batch, nheads_q, nheads_kv, seqlen_q, seqlen_k, head_dim,
+                _lib.strides3(q), _lib.strides3(k), _lib.strides3(v), _lib.strides3(o),
+                seqlen_q_rounded, softmax_scale, int(bool(causal)), encode_dtype(q))
+        if bias is None and not dropout_p:
+            code = lib.fa2_sm100_fwd(*args, _stream_ptr(q.device))
+        else:
+            code = lib.fa2_sm100_fwd_ext(*args, *_lib.bias_args(bias), float(dropout_p), int(dropout_seed),
+                                         _stream_ptr(q.device))
     _lib.check(code, "fa2_sm100_fwd")
     return o, lse, softmax_scale, dropout_seed

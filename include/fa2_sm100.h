@@ -7,6 +7,9 @@
  *   fa2_sm100_fwd            <- `_fwd_kernel[grid](...)`       src/forward/caller.py:83-116
  *   fa2_sm100_bwd_delta      <- `_compute_delta[grid](...)`    src/backward/caller.py:94-114
  *   fa2_sm100_bwd            <- `_bwd_kernel[grid](...)`       src/backward/caller.py:118-160
+ *   fa2_sm100_fwd_ext / fa2_sm100_bwd_ext: the same two launch sites with the reference's optional arguments
+ *                               `bias` (src/forward/caller.py:66, 89, 97) and forward dropout (`dropout_p`,
+ *                               `dropout_seed`, src/forward/caller.py:67, 91-92)
  *   fa2_sm100_dq_convert     <- the fp32 `dq` the reference allocates at src/backward/caller.py:86
  *                               (in the atomic modes our dQ accumulator is an opaque tile-swizzled workspace; this
  *                               call turns it into the caller-visible [B, Sq, Hq, D] tensor)
@@ -39,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 7
+#define FA2_SM100_ABI_VERSION 8
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -76,6 +79,24 @@ int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   const int64_t o_strides[3], int64_t lse_row_stride,
                   float softmax_scale, int causal, int dtype, void* stream);
 
+/* fa2_sm100_fwd with the reference's optional score modifiers (either may be off):
+ *   bias          additive attention bias, logically [B, Hq, Sq, Sk] with a contiguous last dimension, added to the scaled
+ *                 scores before the softmax (src/forward/compute_row_blocks.py:48-54, 68-69). `bias_strides` = (batch,
+ *                 head, row) strides in elements; 0 for a dimension of size 1 that broadcasts. `bias_dtype` = `dtype` or
+ *                 32 (fp32). NULL: no bias. -inf entries act as a mask.
+ *   dropout_p     in [0, 1): each probability is dropped iff tl.rand(dropout_seed, linear index in [B, Hq, Sq, Sk]) <= p
+ *                 - Triton's Philox-4x32-10 stream, bit-identical to the reference's mask (src/forward/
+ *                 compute_row_blocks.py:76-79, tests/utils.py:169-207) - after the row sum was taken, and O is scaled by
+ *                 1 / (1 - p) (src/forward/kernel.py:256-257). The LSE is that of the undropped row. 0: no dropout.
+ * The reference has no dropout in its backward (src/utils.py:87-88: NotImplementedError); neither has this library. */
+int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, float* lse,
+                      int B, int Hq, int Hkv, int Sq, int Sk, int D,
+                      const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                      const int64_t o_strides[3], int64_t lse_row_stride,
+                      float softmax_scale, int causal, int dtype,
+                      const void* bias, int bias_dtype, const int64_t bias_strides[3],
+                      float dropout_p, uint64_t dropout_seed, void* stream);
+
 /* delta[b, h, i] = sum_d O[b, i, h, d] * dO[b, i, h, d] in fp32; rows in [Sq, lse_row_stride) are set to 0.
  * If `workspace` is not NULL the same launch also zero-fills it (the reference zero-allocates dq at
  * src/backward/caller.py:86); that is the state fa2_sm100_bwd expects to find its workspace in. */
@@ -105,6 +126,19 @@ int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v,
                   const int64_t dv_strides[3],
                   int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype,
                   void* stream);
+
+/* fa2_sm100_bwd with the additive attention bias of the forward (`bias`, `bias_dtype`, `bias_strides` as in
+ * fa2_sm100_fwd_ext; the bias itself gets no gradient, like the reference: src/wrapper.py:86). Every deterministic mode
+ * (1, 3, 4, 5, 6, 7) takes a bias; the fused modes 0 and 2 return FA2_E_BAD_SHAPE when one is passed. */
+int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void* v,
+                      const float* lse, const float* delta,
+                      void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes,
+                      int B, int Hq, int Hkv, int Sq, int Sk, int D,
+                      const int64_t do_strides[3], const int64_t q_strides[3], const int64_t k_strides[3],
+                      const int64_t v_strides[3], const int64_t dq_strides[3], const int64_t dk_strides[3],
+                      const int64_t dv_strides[3],
+                      int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype,
+                      const void* bias, int bias_dtype, const int64_t bias_strides[3], void* stream);
 
 /* dq[b, i, h, :] = softmax_scale * accumulator[b, h, i, :], written as `out_dtype` (16, 17 or 32). Called by
  * fa2_sm100_bwd itself in modes 0 and 2; exported for callers that keep several accumulators in flight. */

@@ -13,12 +13,16 @@ import math
 import torch
 
 
-def flash_attn_reference(q, k, v, causal=False, upcast=True, reorder_ops=False, softmax_scale=None, padding_mask=None):
+def flash_attn_reference(q, k, v, causal=False, upcast=True, reorder_ops=False, softmax_scale=None, padding_mask=None,
+                         attn_bias=None, dropout_p=0.0, dropout_mask=None):
     """q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] -> output [B,Sq,Hq,D] in q's dtype.
 
     padding_mask: optional bool [B, S] used as both query_padding_mask and key_padding_mask, the way the reference's
     tests call it (tests/core.py:31-49): padded keys are hidden (:91-92), the causal diagonal follows the per-sequence
     lengths (:16-29), padded query rows produce zeros (:111-112, :121-122).
+
+    attn_bias: broadcastable to [B, Hq, Sq, Sk], added to the scaled, masked scores (:101-102). dropout_mask: bool
+    [B, Hq, Sq, Sk] keep-mask applied to the softmax output, V scaled by 1 / (1 - dropout_p) (:113-120).
 
     upcast: compute in fp32 (src/reference_implementation.py:77-78). reorder_ops: scale K instead of Q
     (:83-86), used by the reference tests to estimate the error of a same-precision implementation.
@@ -47,27 +51,32 @@ def flash_attn_reference(q, k, v, causal=False, upcast=True, reorder_ops=False, 
         else:  # per-sequence lengths; query and key lengths coincide, so the diagonal is the main one
             hidden = (col > row).expand(q.shape[0], 1, sq, sk)
         scores = scores.masked_fill(hidden, float("-inf"))
+    if attn_bias is not None:
+        scores = scores + attn_bias.to(scores.dtype)
     attn = torch.softmax(scores, dim=-1).to(v.dtype)  # :105
     if hidden is not None:  # rows without any visible key: 0 instead of NaN (:107-108)
         attn = attn.masked_fill(torch.all(hidden, dim=-1, keepdim=True), 0.0)
     if padding_mask is not None:
         attn = attn.masked_fill((~padding_mask).unsqueeze(1).unsqueeze(-1), 0.0)
-    out = torch.einsum("bhts,bshd->bthd", attn, v)  # :120
+    if dropout_mask is not None:
+        attn = attn.masked_fill(~dropout_mask, 0.0)
+    out = torch.einsum("bhts,bshd->bthd", attn, v * (1.0 / (1.0 - dropout_p)))  # :120
     if padding_mask is not None:
         out = out.masked_fill((~padding_mask).unsqueeze(-1).unsqueeze(-1), 0.0)
     return out.to(out_dtype)
 
 
-def fwd_bwd(q, k, v, do, causal=False, upcast=True, reorder_ops=False, padding_mask=None, softmax_scale=None):
+def fwd_bwd(q, k, v, do, causal=False, upcast=True, reorder_ops=False, padding_mask=None, softmax_scale=None,
+            attn_bias=None):
     """Forward + autograd backward: (out, dq, dk, dv). Inputs are left untouched."""
     q, k, v = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
     out = flash_attn_reference(q, k, v, causal=causal, upcast=upcast, reorder_ops=reorder_ops, padding_mask=padding_mask,
-                               softmax_scale=softmax_scale)
+                               softmax_scale=softmax_scale, attn_bias=attn_bias)
     dq, dk, dv = torch.autograd.grad(out, (q, k, v), do)
     return out.detach(), dq, dk, dv
 
 
-def lse_log2(q, k, causal=False, softmax_scale=None):
+def lse_log2(q, k, causal=False, softmax_scale=None, attn_bias=None):
     """fp32 log2-domain logsumexp [B, Hq, Sq] - the quantity the forward kernel saves
     (src/forward/kernel.py:119; tests/test_logsumexp.py:53-74 states the same definition)."""
     q, k = q.float(), k.float()
@@ -81,4 +90,6 @@ def lse_log2(q, k, causal=False, softmax_scale=None):
         row = torch.arange(sq, device=q.device).unsqueeze(-1)
         col = torch.arange(sk, device=q.device)
         scores = scores.masked_fill(col > row + (sk - sq), float("-inf"))
+    if attn_bias is not None:
+        scores = scores + attn_bias.float()
     return torch.logsumexp(scores, dim=-1) * 1.4426950408889634

@@ -47,4 +47,27 @@ def load_golden(name):
 
 
 def golden_names():
-    return sorted(p.stem for p in GOLDEN.glob("*.npz"))
+    """Fixtures from the reference's eager oracle (oracle/gen_golden.py)."""
+    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith("triton_"))
+
+
+def triton_golden_names(with_backward=None):
+    """Fixtures from the reference's Triton kernels under Triton's CPU interpreter (oracle/gen_golden_triton.py).
+    The forward-dropout cases hold no gradients (the reference's backward raises under dropout)."""
+    names = sorted(p.stem for p in GOLDEN.glob("triton_*.npz"))
+    if with_backward is None:
+        return names
+    return [n for n in names if ("dropout" not in n) == with_backward]
+
+
+def triton_golden_extras(g):
+    """(seqlens or None, bias or None, keep-mask or None, dropout_p) of a Triton fixture."""
+    B, Sq, H, _ = g["q"].shape
+    Sk = g["k"].shape[1]
+    seqlens = g["attention_mask"].sum(axis=1) if "attention_mask" in g else None
+    bias = g.get("bias")
+    keep, p = None, 0.0
+    if "dropout_keep" in g:
+        keep = np.unpackbits(g["dropout_keep"])[: B * H * Sq * Sk].astype(bool).reshape(B, H, Sq, Sk)
+        p = float(g["dropout_p"])
+    return seqlens, bias, keep, p

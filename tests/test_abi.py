@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/fa2_sm100.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.fa2_sm100_version() == 7
+    assert lib.fa2_sm100_version() == 8
 
 
 def test_workspace_size_formula():
@@ -90,8 +90,12 @@ def test_cpu_tensors_are_rejected_like_the_reference():
         pkg.flash_attn_func(q, q, q)
     with pytest.raises(AssertionError):  # src/forward/caller.py:40 dtype check
         pkg.flash_attn_func(q.float(), q.float(), q.float())
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):  # dropout does not change that
         pkg.flash_attn_func(q, q, q, dropout_p=0.1)
+    with pytest.raises(AssertionError):  # src/utils.py:81-82
+        pkg.flash_attn_func(q, q, q, dropout_p=1.0)
+    with pytest.raises(NotImplementedError):  # src/utils.py:87-88: no dropout in the backward pass
+        pkg._flash_attn_backward(q, q, q, q, None, None, q, torch.zeros(1, 2, 128), 0.1, False, None, 1)
 
 
 def test_product_package_does_not_import_the_oracle():
