@@ -347,9 +347,29 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float4* lse_s = reinterpret_cast<const float4*>(sLse + qs * kBlk + wg * kCmpCols);
       const float4* delta_s = reinterpret_cast<const float4*>(sDelta + ds * kBlk + wg * kCmpCols);
       const bool need_mask = (kv0 + kBlk > p.Sk) || (m * kBlk + kBlk > p.Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
-      int64_t bias_head_off = 0;
-      if constexpr (kBias) bias_head_off = batch * p.bias.sb + (head_kv * group + it / m_count) * p.bias.sh;
-      (void)bias_head_off;
+      // kBias: this thread's 32 bias values bias[q0 + j][kv] (one coalesced 64-byte warp load per query row), fetched
+      // before the waits below so that their latency hides behind the S^T product; scaled to the log2 domain.
+      // 16-bit values travel as packed pairs, fp32 ones unpacked.
+      uint32_t braw[kCmpCols];
+      if constexpr (kBias) {
+        const int64_t off0 = batch * p.bias.sb + (head_kv * group + it / m_count) * p.bias.sh +
+                             static_cast<int64_t>(q0) * p.bias.sm + kv;
+        const bool col_ok = kv < p.Sk;
+        if (p.bias.is_fp32) {
+          const float* bp = static_cast<const float*>(p.bias.ptr) + off0;
+#pragma unroll
+          for (int j = 0; j < kCmpCols; ++j)
+            braw[j] = (col_ok && q0 + j < p.Sq) ? __float_as_uint(__ldg(bp + j * p.bias.sm)) : 0u;
+        } else {
+          const uint16_t* bp = static_cast<const uint16_t*>(p.bias.ptr) + off0;
+#pragma unroll
+          for (int j = 0; j < kCmpCols; j += 2) {
+            const uint32_t lo = (col_ok && q0 + j < p.Sq) ? __ldg(bp + j * p.bias.sm) : 0u;
+            const uint32_t hi = (col_ok && q0 + j + 1 < p.Sq) ? __ldg(bp + (j + 1) * p.bias.sm) : 0u;
+            braw[j / 2] = lo | (hi << 16);
+          }
+        }
+      }
 
       // ---- P^T = exp2(S^T * c - LSE) = exp2(-(LSE - S^T * c)) ----
       if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 0);
@@ -377,9 +397,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int qi = q0 + j + e;
-            float b = 0.f;
-            if (qi < p.Sq && kv < p.Sk) b = bias_load<kBf16>(p.bias, bias_head_off + static_cast<int64_t>(qi) * p.bias.sm + kv);
+            float b;
+            if (p.bias.is_fp32) b = __uint_as_float(braw[j + e]);
+            else b = bias_to_float<kBf16>(static_cast<uint16_t>((braw[(j + e) / 2] >> (16 * (e % 2))) & 0xffffu));
             tt[e] = fmaf(b, -1.4426950408889634f, tt[e]);
             tt[e] = (ll[e] == -INFINITY) ? INFINITY : tt[e];
           }

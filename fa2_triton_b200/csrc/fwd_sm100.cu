@@ -92,7 +92,7 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between
 #define FA2_FWD_SPEC 0
 #endif
 
-template <int D>
+template <int D, bool kExt = false>
 struct FwdSmem {
   static constexpr int kStages = (D == 128) ? 2 : 4;
   static constexpr int kTileBytes = kBM * D * 2;  // Q, K and V tiles all have 128 rows
@@ -105,8 +105,14 @@ struct FwdSmem {
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
   // row statistics exchanged between the kHalves threads of a row: [parity 2 x kind 2][tile 2][half 2][128 rows] fp32
   static constexpr int kXchgOff = kTmemSlotOff + 16;
-  static constexpr int kBytes = kXchgOff + 4 * 2 * 2 * kBM * 4;
+  // kExt: per softmax warp, a staging tile for the attention bias - 32 rows x 64 bytes, rows 80 bytes apart so that
+  // both the coalesced writes (8 rows x 64 B per instruction) and the row-per-lane 16-byte reads are conflict-free
+  static constexpr int kStageOff = (kXchgOff + 4 * 2 * 2 * kBM * 4 + 15) / 16 * 16;
+  static constexpr int kStageRow = 80;
+  static constexpr int kStageWarpBytes = 32 * kStageRow;
+  static constexpr int kBytes = kStageOff + (kExt ? (kSmxThreads / 32) * kStageWarpBytes : 0);
   static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-byte alignment
+  static_assert(kDynBytes <= 227 * 1024, "forward shared memory exceeds the 227 KB a CTA can have");
 };
 
 // number of key blocks query tile [row0, row0+128) has to visit
@@ -119,13 +125,13 @@ __device__ __forceinline__ int num_kv_blocks(int row0, int Sq, int Sk, int causa
 
 }  // namespace
 
-// kExt: the variant with additive bias and / or dropout (runtime: p.bias.ptr, p.dropout_p), see extras.cuh
-template <int D, bool kBf16, bool kExt>
+// kExt: variants with an additive bias (bit 0) and / or forward dropout (bit 1), see extras.cuh; 0 = the plain kernel
+template <int D, bool kBf16, int kExt>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                const FwdParams p) {
-  using L = FwdSmem<D>;
+  using L = FwdSmem<D, (kExt & 1) != 0>;
   constexpr int kStages = L::kStages;
   constexpr int kSub = D / 64;           // 64-column (128-byte) sub-tiles per row
   constexpr int kSubBytes = kBM * 128;   // one [128 x 64] 16-bit sub-tile
@@ -331,9 +337,131 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
     for (int i = 0; i < nblk; ++i) {
       if (r == 0 && half == 0) FA2_STAMP(t, i, 0);
+      // ---- kExt: additive bias (src/forward/compute_row_blocks.py:48-54, 68-69) ----
+      // It joins the raw scores as bias / softmax_scale, so that the common factor c = softmax_scale * log2(e) applies
+      // to both; hidden entries are set to -inf afterwards. A thread owns a score row, so reading its 128 bias values
+      // straight from global memory makes every warp load touch 32 different lines (measured: forward 7.5x slower),
+      // and loading piecewise after the scores have arrived exposes the L2 latency 16 times per block (5x slower).
+      // So: (1) BEFORE waiting for S, each warp fetches the block's bias for its 32 rows with coalesced 16-byte loads
+      // (8 rows x 64 B per instruction) into registers - the score registers are not live yet and the latency hides
+      // behind the Q K^T product; (2) once S is there, 64-byte pieces of the rows go through a warp-private staging
+      // tile in shared memory, every lane reads its own row back, adds it to its scores IN TENSOR MEMORY and the
+      // usual path below takes over. (Everything unrolled at once made the kernel 17 000 instructions long and
+      // instruction-cache bound; the loops below are sized to stay at ~5 000.)
+      uint4 breg[16];
+      bool bias_fast = false;
+      [[maybe_unused]] const int bias_col0 = i * kBN;
+      [[maybe_unused]] const int wrow0 = tile_row0 + (warp & 3) * 32;  // first query row of this warp
+      [[maybe_unused]] auto bias_fetch = [&](auto elem_tag, int group) {
+        constexpr int kElem = decltype(elem_tag)::value;  // bytes per bias element: 2 or 4
+        constexpr int kChunkCols = 64 / kElem;            // columns per 64-byte piece of a row
+        constexpr int kPer16 = 16 / kElem;                // elements per 16-byte load
+        const uint8_t* base = static_cast<const uint8_t*>(p.bias.ptr);
+        const int64_t head_off = batch * p.bias.sb + head * p.bias.sh;
+        const int gc0 = bias_col0 + group * 4 * kChunkCols;
+        // whole pieces in bounds and 16-byte aligned for every row of the warp (warp-uniform)
+        bias_fast = (wrow0 + 32 <= p.Sq) && (bias_col0 + kBN <= p.Sk) && ((p.bias.sm * kElem) % 16 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(base) + (head_off + bias_col0) * kElem) % 16 == 0);
+#pragma unroll
+        for (int li = 0; li < 16; ++li) {
+          const int ch = li / 4, rr = (li % 4) * 8 + (lane >> 2), piece = lane & 3;
+          const int grow = wrow0 + rr;
+          const int gcol = gc0 + ch * kChunkCols + piece * kPer16;
+          const int64_t idx = head_off + static_cast<int64_t>(grow) * p.bias.sm + gcol;
+          if (bias_fast) {
+            breg[li] = __ldg(reinterpret_cast<const uint4*>(base + idx * kElem));
+          } else {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int e = 0; e < kPer16; ++e) {
+              const bool ok = grow < p.Sq && gcol + e < p.Sk;
+              if constexpr (kElem == 4) w[e] = ok ? __ldg(reinterpret_cast<const uint32_t*>(base) + idx + e) : 0u;
+              else w[e / 2] |= (ok ? static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t*>(base) + idx + e)) : 0u) << (16 * (e % 2));
+            }
+            breg[li] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      };
+      [[maybe_unused]] auto bias_apply = [&](auto elem_tag, int group) {
+        constexpr int kElem = decltype(elem_tag)::value;
+        constexpr int kChunkCols = 64 / kElem;
+        uint8_t* stage = smem + L::kStageOff + warp * L::kStageWarpBytes;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+          for (int li = 0; li < 4; ++li)
+            *reinterpret_cast<uint4*>(stage + (li * 8 + (lane >> 2)) * L::kStageRow + (lane & 3) * 16) = breg[ch * 4 + li];
+          __syncwarp();
+          uint4 mine[4];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) mine[k4] = *reinterpret_cast<const uint4*>(stage + lane * L::kStageRow + k4 * 16);
+          __syncwarp();
+          const uint32_t tcol = tS + (group * 4 + ch) * kChunkCols;
+          uint32_t sv[kChunkCols];
+          if constexpr (kChunkCols == 32) tmem_ld_32x32b_x32(tcol, sv); else tmem_ld_32x32b_x16(tcol, sv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t w[4] = {mine[k4].x, mine[k4].y, mine[k4].z, mine[k4].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if constexpr (kElem == 4) {
+                const int j = k4 * 4 + e;
+                sv[j] = __float_as_uint(fmaf(__uint_as_float(w[e]), p.bias_mul, __uint_as_float(sv[j])));
+              } else {
+                const int j = k4 * 8 + 2 * e;
+                sv[j] = __float_as_uint(fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] & 0xffffu)), p.bias_mul, __uint_as_float(sv[j])));
+                sv[j + 1] = __float_as_uint(fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] >> 16)), p.bias_mul, __uint_as_float(sv[j + 1])));
+              }
+            }
+          }
+          if constexpr (kChunkCols == 32) tmem_st_32x32b_x32(tcol, sv); else tmem_st_32x32b_x16(tcol, sv);
+        }
+      };
+      if constexpr ((kExt & 1) && kHalves == 1) {
+        if (p.bias.ptr != nullptr) {
+          if (p.bias.is_fp32) bias_fetch(std::integral_constant<int, 4>{}, 0);
+          else bias_fetch(std::integral_constant<int, 2>{}, 0);
+        }
+      }
+      // ---- kExt bit 1: dropout. One keep bit per score of this thread's row and block, drawn here, before the scores
+      // arrive: the registers are free and the Philox rounds fill the wait for the Q K^T product. They stay in a
+      // rolled loop (see the note on code size above).
+      uint32_t keep_bits[kCols / 32];
+      if constexpr ((kExt & 2) != 0) {
+#pragma unroll
+        for (int wd = 0; wd < kCols / 32; ++wd) {
+          uint32_t bits = 0xffffffffu;
+          if (p.dropout_p > 0.f) {
+            bits = 0u;
+            const uint32_t off = drop_row_off + static_cast<uint32_t>(i * kBN + half * kCols + wd * 32);
+#pragma unroll 2
+            for (int b = 0; b < 32; ++b)
+              bits |= static_cast<uint32_t>(dropout_keep(p.seed_lo, p.seed_hi, off + b, p.dropout_p)) << b;
+          }
+          keep_bits[wd] = bits;
+        }
+      }
+      (void)keep_bits;
       mbar_wait(&s_full[t], i & 1);
       tcgen05_fence_after();
       if (r == 0 && half == 0) FA2_STAMP(t, i, 1);
+      if constexpr ((kExt & 1) != 0) {
+        if (p.bias.ptr != nullptr) {
+          if constexpr (kHalves == 1) {
+            if (p.bias.is_fp32) {  // 64 columns per pass: the second fetch is exposed (fp32 biases are the rare case)
+              bias_apply(std::integral_constant<int, 4>{}, 0);
+              bias_fetch(std::integral_constant<int, 4>{}, 1);
+              bias_apply(std::integral_constant<int, 4>{}, 1);
+            } else {
+              bias_apply(std::integral_constant<int, 2>{}, 0);
+            }
+            tmem_wait_st();
+          } else {
+            __trap();  // the staged bias path assumes one softmax thread per row (FA2_FWD_HALVES = 1, the default)
+          }
+        }
+      }
 
       float s[kCols];  // this thread's part of the score row
       auto load_scores = [&]() {
@@ -354,32 +482,6 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
 #pragma unroll
         for (int j = 0; j < kCols; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
-      }
-
-      if constexpr (kExt) {
-        // additive bias (src/forward/compute_row_blocks.py:48-54, 68-69): joins the raw scores as bias / softmax_scale,
-        // so that the common factor c = softmax_scale * log2(e) applies to both; hidden entries stay at -inf
-        if (p.bias.ptr != nullptr && row < p.Sq) {
-          const int64_t off = batch * p.bias.sb + head * p.bias.sh + static_cast<int64_t>(row) * p.bias.sm + col0;
-          const int n_valid = p.Sk - col0;  // columns of this block that exist
-          const uint16_t* b16 = static_cast<const uint16_t*>(p.bias.ptr) + off;
-          if (!p.bias.is_fp32 && n_valid >= kCols && (reinterpret_cast<uintptr_t>(b16) & 15u) == 0) {
-#pragma unroll
-            for (int j = 0; j < kCols; j += 8) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(b16 + j));
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                s[j + 2 * e] = fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] & 0xffffu)), p.bias_mul, s[j + 2 * e]);
-                s[j + 2 * e + 1] = fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] >> 16)), p.bias_mul, s[j + 2 * e + 1]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < kCols; ++j)
-              if (j < n_valid) s[j] = fmaf(bias_load<kBf16>(p.bias, off + j), p.bias_mul, s[j]);
-          }
-        }
       }
 
       uint32_t pk[kCols / 2];
@@ -508,13 +610,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           ls[j % 4] += pr[0];
           ls[j % 4 + 1] += pr[1];
-          if constexpr (kExt) {
+          if constexpr ((kExt & 2) != 0) {
             // dropout hits P after its row sum was taken (src/forward/compute_row_blocks.py:73-79)
-            if (p.dropout_p > 0.f) {
-              const uint32_t off = drop_row_off + static_cast<uint32_t>(col0 + j);
-              pr[0] = dropout_keep(p.seed_lo, p.seed_hi, off, p.dropout_p) ? pr[0] : 0.f;
-              pr[1] = dropout_keep(p.seed_lo, p.seed_hi, off + 1u, p.dropout_p) ? pr[1] : 0.f;
-            }
+            pr[0] = ((keep_bits[j / 32] >> (j % 32)) & 1u) ? pr[0] : 0.f;
+            pr[1] = ((keep_bits[(j + 1) / 32] >> ((j + 1) % 32)) & 1u) ? pr[1] : 0.f;
           }
 #else
 #pragma unroll
@@ -558,7 +657,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         l += *xchg_slot(nblk & 1, half ^ 1);
       }
       float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
-      if constexpr (kExt) {
+      if constexpr ((kExt & 2) != 0) {
         if (p.dropout_p > 0.f) inv_l *= p.inv_keep;  // src/forward/kernel.py:256-257
       }
       if (nblk > 0) {
@@ -621,11 +720,11 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int D, bool kBf16, bool kExt>
+template <int D, bool kBf16, int kExt>
 static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                 const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
   auto kernel = fa2_fwd_kernel<D, kBf16, kExt>;
-  constexpr int smem = FwdSmem<D>::kDynBytes;
+  constexpr int smem = FwdSmem<D, (kExt & 1) != 0>::kDynBytes;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -647,10 +746,17 @@ cudaError_t fetch_fwd_trace(long long* host, size_t n) {
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
-  const bool ext = p.bias.ptr != nullptr || p.dropout_p > 0.f;
-#define FA2_FWD_CASE(d, b, e) if (D == d && bf16 == b && ext == e) return launch_fwd_t<d, b, e>(tq, tk, tv, to, p, stream);
-  FA2_FWD_CASE(128, true, false) FA2_FWD_CASE(128, false, false) FA2_FWD_CASE(64, true, false) FA2_FWD_CASE(64, false, false)
-  FA2_FWD_CASE(128, true, true) FA2_FWD_CASE(128, false, true) FA2_FWD_CASE(64, true, true) FA2_FWD_CASE(64, false, true)
+  const int ext = (p.bias.ptr != nullptr ? 1 : 0) | (p.dropout_p > 0.f ? 2 : 0);
+#define FA2_FWD_CASE(d, b)                                                                       \
+  if (D == d && bf16 == b) {                                                                     \
+    switch (ext) {                                                                               \
+      case 0: return launch_fwd_t<d, b, 0>(tq, tk, tv, to, p, stream);                           \
+      case 1: return launch_fwd_t<d, b, 1>(tq, tk, tv, to, p, stream);                           \
+      case 2: return launch_fwd_t<d, b, 2>(tq, tk, tv, to, p, stream);                           \
+      default: return launch_fwd_t<d, b, 3>(tq, tk, tv, to, p, stream);                          \
+    }                                                                                            \
+  }
+  FA2_FWD_CASE(128, true) FA2_FWD_CASE(128, false) FA2_FWD_CASE(64, true) FA2_FWD_CASE(64, false)
 #undef FA2_FWD_CASE
   return cudaErrorInvalidValue;
 }
