@@ -11,7 +11,7 @@ from torch import Tensor
 
 from . import _lib
 from .forward import (SUPPORTED_HEAD_DIMS, _stream_ptr, check_bias, encode_dtype, handle_dropout, pad_last,
-                      padded_head_dim, sequence_lengths)
+                      padded_head_dim, runs_natively, sequence_lengths)
 
 # Process-wide default for how dQ contributions are summed.
 #   True     : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
@@ -89,7 +89,11 @@ def _flash_attn_backward(
                 if dst is not None:
                     dst[b, :n] = src[0]
         return dq, dk, dv
-    if q.shape[-1] not in SUPPORTED_HEAD_DIMS:
+    det_req = _DETERMINISTIC if deterministic is None else deterministic
+    fused_req = bias is None and (det_req is False or (not isinstance(det_req, bool) and det_req in (0, 2)))
+    # zero-padded copies only for head dims TMA cannot address (not a multiple of 8) and for the fused kernel, whose dQ
+    # accumulator layout exists for 64 and 128 only
+    if not runs_natively(q.shape[-1]) or (fused_req and q.shape[-1] not in SUPPORTED_HEAD_DIMS):
         head_dim = q.shape[-1]
         d = padded_head_dim(head_dim)
         scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)

@@ -77,7 +77,8 @@ int make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype, int B, int S, i
 
 int check_common(int B, int Hq, int Hkv, int Sq, int Sk, int D, int dtype) {
   if (!is_16bit(dtype)) return fail(FA2_E_UNSUPPORTED_DTYPE, "dtype code %d: only 16 (fp16) and 17 (bf16) are supported", dtype);
-  if (D != 64 && D != 128) return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: this build supports 64 and 128", D);
+  if (D < 8 || D > 128 || D % 8 != 0)
+    return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: this build supports multiples of 8 up to 128", D);
   if (B < 1 || Hq < 1 || Hkv < 1 || Sq < 1 || Sk < 1) return fail(FA2_E_BAD_SHAPE, "non-positive dimension");
   if (Hq % Hkv != 0) return fail(FA2_E_BAD_SHAPE, "nheads_q = %d is not divisible by nheads_kv = %d", Hq, Hkv);
   if (Hq > 65535 || B > 65535) return fail(FA2_E_BAD_SHAPE, "batch and head counts must fit a grid dimension");
@@ -106,6 +107,10 @@ int make_bias_view(fa2::BiasView* view, const void* bias, int bias_dtype, const 
 }
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// The kernels are instantiated for head dims 64 and 128. Any multiple of 8 below runs in the next instantiation: the
+// tensor maps carry the real head dim, so TMA zero-fills the missing columns on load and clips them on store.
+int kernel_head_dim(int D) { return D <= 64 ? 64 : 128; }
 
 }  // namespace
 
@@ -151,7 +156,7 @@ int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, floa
   p.inv_keep = 1.0f / (1.0f - dropout_p);
   p.seed_lo = static_cast<uint32_t>(dropout_seed & 0xffffffffull);
   p.seed_hi = static_cast<uint32_t>(dropout_seed >> 32);
-  cudaError_t ce = fa2::launch_fwd(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, to, p, static_cast<cudaStream_t>(stream));
+  cudaError_t ce = fa2::launch_fwd(kernel_head_dim(D), dtype == FA2_DTYPE_BF16, tq, tk, tv, to, p, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_fwd launch");
   return 0;
 }
@@ -172,6 +177,8 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, in
   p.lse_stride = static_cast<int>(lse_row_stride);
   for (int i = 0; i < 3; ++i) { p.o_strides[i] = o_strides[i]; p.do_strides[i] = do_strides[i]; }
   if (workspace) {
+    if (D != kernel_head_dim(D))
+      return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: the dQ accumulator of the fused backward needs 64 or 128", D);
     const size_t need = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, 1, D, 0, FA2_DQ_ATOMIC);
     if (workspace_bytes < need)
       return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
@@ -226,6 +233,10 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
   fa2::BiasView bias_view{};
   if (int e = make_bias_view(&bias_view, bias, bias_dtype, bias_strides, dtype)) return e;
+  const int Dk = kernel_head_dim(D);
+  if (D != Dk && (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED))
+    return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: the fused (atomic / ticket-ordered) backward needs 64 or 128; "
+                                            "the deterministic modes take any multiple of 8 up to 128", D);
   if (bias && (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED))
     return fail(FA2_E_BAD_SHAPE, "bias: the fused (atomic / ticket-ordered) backward has no bias variant; use a "
                                  "deterministic mode (1, 3, 4, 5, 6)");
@@ -292,7 +303,7 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
     static const bool old_dkdv = [] { const char* e = getenv("FA2_SM100_OLD_DKDV"); return e && e[0] == '1'; }();
     static const bool nonpersistent = [] { const char* e = getenv("FA2_SM100_DKDV_PERSISTENT"); return !(e && e[0] == '1'); }();
     if (fused || (old_dkdv && !spill && !bias)) {
-      ce = fa2::launch_bwd(D, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
+      ce = fa2::launch_bwd(Dk, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
     } else {
       fa2::DkdvParams k{};
       k.lse = lse; k.delta = delta;
@@ -309,8 +320,8 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
       k.max_ctas = dkdv_ctas;  // experiments only (scripts/concurrent_probe.py): cap on the persistent grid
       for (int i = 0; i < 3; ++i) { k.dk_strides[i] = dk_strides[i]; k.dv_strides[i] = dv_strides[i]; }
       k.bias = bias_view;
-      if (nonpersistent || bias) ce = fa2::launch_bwd_dkdv(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
-      else ce = fa2::launch_bwd_dkdv_persistent(D, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
+      if (nonpersistent || bias || D != Dk) ce = fa2::launch_bwd_dkdv(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
+      else ce = fa2::launch_bwd_dkdv_persistent(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
   }
@@ -333,7 +344,8 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
     d.causal = causal ? 1 : 0;
     static const int dq_ctas = [] { const char* e = getenv("FA2_SM100_DQ_CTAS"); return e ? atoi(e) : 0; }();
     d.max_ctas = dq_ctas;  // experiments only: cap on the persistent grid
-    ce = fa2::launch_bwd_dq_spill(D, dtype == FA2_DTYPE_BF16, tk, d, st);
+    d.d_actual = D;
+    ce = fa2::launch_bwd_dq_spill(Dk, dtype == FA2_DTYPE_BF16, tk, d, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ (spill) launch");
     return 0;
   }
@@ -351,7 +363,8 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
   d.scale_log2 = softmax_scale * kLog2e;
   d.causal = causal ? 1 : 0;
   d.bias = bias_view;
-  ce = fa2::launch_bwd_dq(D, dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, tdq, d, st);
+  d.d_actual = D;
+  ce = fa2::launch_bwd_dq(Dk, dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, tdq, d, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ launch");
   return 0;
 }

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
   for (int i = 0; i < kPasses; ++i) {
     const int row = row0 + i * kRowsPerPass;
     ov[i] = gv[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < p.Sq) {
+    if (row < p.Sq && part * 8 < p.D) {  // p.D < D: the tensors' head dim is zero-padded up to the kernel's
       ov[i] = *reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(row) * p.o_strides[2]);
       gv[i] = *reinterpret_cast<const uint4*>(gbase + static_cast<int64_t>(row) * p.do_strides[2]);
     }
@@ -164,12 +164,15 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
 }
 
 cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream) {
-  const int rows_per_block = 4 * (256 / (p.D / 8));
+  const int dk = p.D <= 64 ? 64 : 128;  // instantiation; head dims in between are handled by the column guard
+  const int rows_per_block = 4 * (256 / (dk / 8));
   dim3 grid((p.lse_stride + rows_per_block - 1) / rows_per_block, p.Hq, p.B);
-  if (p.D == 128) {
+  if (p.D < 8 || p.D > 128 || p.D % 8) return cudaErrorInvalidValue;
+  if (p.dq_accum != nullptr && p.D != dk) return cudaErrorInvalidValue;  // the accumulator layout needs D in {64, 128}
+  if (dk == 128) {
     if (bf16) fa2_delta_kernel<128, true><<<grid, 256, 0, stream>>>(p);
     else fa2_delta_kernel<128, false><<<grid, 256, 0, stream>>>(p);
-  } else if (p.D == 64) {
+  } else if (dk == 64) {
     if (bf16) fa2_delta_kernel<64, true><<<grid, 256, 0, stream>>>(p);
     else fa2_delta_kernel<64, false><<<grid, 256, 0, stream>>>(p);
   } else {

@@ -37,7 +37,7 @@ struct DeltaParams {
   const void* o;
   const void* dout;
   float* delta;  // [B, Hq, lse_stride]
-  int B, Hq, Sq, D;
+  int B, Hq, Sq, D;       // D: the tensors' head dim (a multiple of 8, <= 128); the kernel is instantiated for 64 or 128
   int lse_stride;
   int64_t o_strides[3];   // batch, head, seq (elements)
   int64_t do_strides[3];
@@ -79,6 +79,7 @@ struct DqParams {
   float scale_log2;
   int causal;
   BiasView bias;       // kernel variant kBias; ptr == nullptr otherwise
+  int d_actual;        // head dim of the tensors (multiple of 8, <= the kernel's D): columns beyond it are not stored
 };
 cudaError_t launch_bwd_dq(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           const CUtensorMap& tdo, const CUtensorMap& tdq, const DqParams& p, cudaStream_t stream);
@@ -150,6 +151,7 @@ struct DqSpillParams {
   float softmax_scale;
   int causal;
   int max_ctas;        // > 0: cap on the persistent grid
+  int d_actual;        // head dim of the tensors (multiple of 8, <= the kernel's D): columns beyond it are not stored
 };
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream);
 

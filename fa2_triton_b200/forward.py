@@ -26,13 +26,19 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-SUPPORTED_HEAD_DIMS = (64, 128)
+SUPPORTED_HEAD_DIMS = (64, 128)  # the kernel instantiations
+
+
+def runs_natively(head_dim: int) -> bool:
+    """Head dims that go to the kernels as they are: multiples of 8 up to 128. TMA zero-fills the columns between the
+    tensor's head dim and the kernel's (64 or 128) on load and clips them on store - no padded copies."""
+    return 8 <= head_dim <= SUPPORTED_HEAD_DIMS[-1] and head_dim % 8 == 0
 
 
 def padded_head_dim(head_dim: int) -> int:
-    """The kernels exist for D = 64 and 128; any smaller head dim runs zero-padded to the next of the two (zero
-    columns add nothing to Q K^T and produce zero columns of O, dQ, dK, dV). The reference pads to the next power of
-    two inside its kernels the same way (src/forward/caller.py:77-78, PADDED_HEADS)."""
+    """Any other head dim up to 128 (odd ones like 59 or 111: TMA needs 16-byte strides) runs on zero-padded copies of
+    the next kernel head dim: zero columns add nothing to Q K^T and produce zero columns of O, dQ, dK, dV. The reference
+    pads to the next power of two inside its kernels the same way (src/forward/caller.py:77-78, PADDED_HEADS)."""
     for d in SUPPORTED_HEAD_DIMS:
         if head_dim <= d:
             return d
@@ -124,7 +130,7 @@ def _flash_attn_forward(
                                                scale, dropout_seed, out=o[b:b + 1, :n])
             lse[b, :, :lb.shape[-1]] = lb[0]
         return o, lse, scale, 0 if dropout_seed is None else dropout_seed
-    if head_dim not in SUPPORTED_HEAD_DIMS:
+    if not runs_natively(head_dim):
         d = padded_head_dim(head_dim)
         scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
         o, lse, _, seed = _flash_attn_forward(pad_last(q, d), pad_last(k, d), pad_last(v, d), None, bias, dropout_p,

@@ -29,8 +29,10 @@
  *     fa2_sm100_last_error() returns a thread-local description of the last failure.
  *   - thread safety: calls may be made concurrently from different host threads.
  *
- * Supported in this build: D in {64, 128}; Hq % Hkv == 0; any Sq, Sk >= 1; base pointers 16-byte aligned and
- * every stride a multiple of 8 elements (TMA requirement).
+ * Supported in this build: head dims D = 8, 16, ..., 128 (the kernels exist for 64 and 128; a smaller multiple of 8 runs
+ * in the next one, TMA zero-filling the missing columns - the reference pads to a power of two inside its kernels the
+ * same way, src/forward/caller.py:77-78; the fused backward modes 0 and 2 need 64 or 128); Hq % Hkv == 0; any Sq, Sk >= 1;
+ * base pointers 16-byte aligned and every stride a multiple of 8 elements (TMA requirement).
  */
 #ifndef FA2_SM100_H_
 #define FA2_SM100_H_

@@ -29,7 +29,7 @@ CASES = [
     ("MQA 32:1 heads", 4, 4096, 4096, 32, 1, 128, torch.bfloat16, True, True, {}),
     ("fp16", 4, 4096, 4096, 32, 32, 128, torch.float16, True, True, {}),
     ("Sq=1024 < Sk=8192 causal (bottom-right)", 4, 1024, 8192, 32, 32, 128, torch.bfloat16, True, True, {}),
-    ("ragged S=4001, head dim 96 (zero-padded to 128)", 4, 4001, 4001, 32, 32, 96, torch.bfloat16, True, True, {}),
+    ("ragged S=4001, head dim 96 (D=128 kernel, TMA zero-fill)", 4, 4001, 4001, 32, 32, 96, torch.bfloat16, True, True, {}),
     ("head dim 64, non-causal", 4, 4096, 4096, 32, 32, 64, torch.bfloat16, False, True, {}),
     ("attention_mask: lengths 4096 / 3000 / 2048 / 1000", 4, 4096, 4096, 32, 32, 128, torch.bfloat16, True, True,
      {"lengths": (4096, 3000, 2048, 1000)}),

@@ -57,8 +57,10 @@ def test_argument_errors_need_no_gpu():
     s = (ctypes.c_int64 * 3)(128 * 8 * 64, 64, 8 * 64)
     buf = ctypes.create_string_buffer(64)
     ptr = (ctypes.addressof(buf) + 15) & ~15
-    rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 40, s, s, s, s, 128, 0.1, 0, 17, None)
-    assert rc == _lib.E_UNSUPPORTED_HEAD_DIM and b"head_dim 40" in lib.fa2_sm100_last_error()
+    rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 44, s, s, s, s, 128, 0.1, 0, 17, None)
+    assert rc == _lib.E_UNSUPPORTED_HEAD_DIM and b"head_dim 44" in lib.fa2_sm100_last_error()
+    rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 136, s, s, s, s, 128, 0.1, 0, 17, None)
+    assert rc == _lib.E_UNSUPPORTED_HEAD_DIM
     rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 3, 128, 128, 64, s, s, s, s, 128, 0.1, 0, 17, None)
     assert rc == _lib.E_BAD_SHAPE
     rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 64, s, s, s, s, 128, 0.1, 0, 32, None)

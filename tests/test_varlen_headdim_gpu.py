@@ -70,13 +70,50 @@ def test_attention_mask_ignores_padded_content():
 
 
 @pytest.mark.parametrize("causal", [False, True])
-@pytest.mark.parametrize("D", [16, 32, 40, 96, 111])
-def test_padded_head_dims_match_oracle(D, causal):
+@pytest.mark.parametrize("D", [8, 16, 24, 32, 40, 59, 72, 80, 96, 104, 111, 120])
+def test_other_head_dims_match_oracle(D, causal):
+    """Multiples of 8 go to the kernels as they are (TMA zero-fills up to the kernel's 64 / 128 columns), the others
+    (59, 111 of the reference's grid, tests/test_fwd_only.py:12) through zero-padded copies."""
     B, Sq, Sk, Hq, Hkv = 2, 200, 328, 4, 2
     q, k, v, do = generate_test_data(B, Sq, Sk, Hq, Hkv, D, torch.bfloat16, DEV, seed=D)
-    if D % 8:  # odd head dims come out of generate_test_data contiguous: fine, padding makes the copies the kernels see
-        assert q.stride(-1) == 1
+    assert q.stride(-1) == 1
     check(ours(q, k, v, do, causal), q, k, v, do, causal)
+
+
+@pytest.mark.parametrize("det", [False, 1, 5, 2])
+@pytest.mark.parametrize("D", [40, 96])
+def test_other_head_dims_every_dq_mode(D, det):
+    """fp32 dQ (the reference's convention, src/backward/caller.py:86) and every way of summing dQ; the fused modes
+    fall back to padded copies, the deterministic ones run on the tensors as they are."""
+    q, k, v, do = generate_test_data(2, 300, 300, 4, 2, D, torch.float16, DEV, seed=D)
+    prev = fa2.is_deterministic()
+    fa2.set_deterministic(det)
+    try:
+        o, lse, scale, seed = fa2._flash_attn_forward(q, k, v, None, None, 0.0, True, None, None)
+        dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, None, o, lse, 0.0, True, scale, seed)
+        torch.cuda.synchronize()
+    finally:
+        fa2.set_deterministic(prev)
+    assert dq.dtype == torch.float32 and dq.shape == q.shape and dk.shape == k.shape
+    ref = er.fwd_bwd(q, k, v, do, causal=True)
+    for name, g, r in (("O", o, ref[0]), ("dQ", dq, ref[1]), ("dK", dk, ref[2]), ("dV", dv, ref[3])):
+        assert_close_16(name, g, r)
+
+
+def test_native_head_dim_strided_views_and_no_stray_writes():
+    """q, k, v as slices of one packed [B, S, 3, H, D] tensor with D = 80, outputs written into slices of larger
+    buffers: nothing outside the D columns may be touched (TMA clips the store at the tensor's head dim)."""
+    B, S, H, D = 2, 260, 3, 80
+    qkv = torch.randn(B, S, 3, H, D, device=DEV, dtype=torch.bfloat16) * 0.5
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    do = torch.randn(B, S, H, D, device=DEV, dtype=torch.bfloat16)
+    big = torch.full((B, S, H, 128), 7.0, device=DEV, dtype=torch.bfloat16)
+    o, lse, scale, seed = fa2._flash_attn_forward(q, k, v, None, None, 0.0, True, None, None, out=big[..., :D])
+    assert (big[..., D:] == 7.0).all()
+    dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, None, o, lse, 0.0, True, scale, seed, dq_dtype=q.dtype)
+    ref = er.fwd_bwd(q, k, v, do, causal=True)
+    for name, g, r in (("O", o, ref[0]), ("dQ", dq, ref[1]), ("dK", dk, ref[2]), ("dV", dv, ref[3])):
+        assert_close_16(name, g, r)
 
 
 def test_head_dim_above_128_is_rejected():
