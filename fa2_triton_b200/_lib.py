@@ -44,6 +44,14 @@ SIGNATURES = {
     "fa2_sm100_fwd_ext": (_c_int, [_c_void_p] * 5 + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 4
                           + [_c_int64, _c_float, _c_int, _c_int]
                           + [_c_void_p, _c_int, ctypes.POINTER(_c_int64), _c_float, ctypes.c_uint64, _c_void_p]),
+    "fa2_sm100_varlen_workspace_bytes": (_c_size_t, [_c_int]),
+    "fa2_sm100_fwd_varlen": (_c_int, [_c_void_p] * 5 + [_c_int] * 5 + [ctypes.POINTER(_c_int64)] * 4
+                             + [_c_int64, _c_float, _c_int, _c_int] + [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "fa2_sm100_bwd_delta_varlen": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)] * 2
+                                   + [_c_int64, _c_int, _c_void_p, _c_void_p]),
+    "fa2_sm100_bwd_varlen": (_c_int, [_c_void_p] * 10 + [_c_size_t] + [_c_int] * 5 + [ctypes.POINTER(_c_int64)] * 7
+                             + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_int]
+                             + [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "fa2_sm100_bwd_delta": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)] * 2
                             + [_c_int64, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "fa2_sm100_bwd_workspace_bytes": (_c_size_t, [_c_int] * 7),

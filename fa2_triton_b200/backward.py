@@ -10,8 +10,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .forward import (SUPPORTED_HEAD_DIMS, _stream_ptr, check_bias, encode_dtype, handle_dropout, pad_last,
-                      padded_head_dim, runs_natively, sequence_lengths)
+from .forward import (SUPPORTED_HEAD_DIMS, _stream_ptr, check_bias, device_sequence_lengths, encode_dtype, handle_dropout,
+                      pad_last, padded_head_dim, runs_natively, sequence_lengths, varlen_in_kernel)
 
 # Process-wide default for how dQ contributions are summed.
 #   True     : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
@@ -40,6 +40,54 @@ def _spill_limit_bytes() -> int:
 
 def is_deterministic() -> bool:
     return _DETERMINISTIC
+
+
+def _backward_varlen(dO, q, k, v, attention_mask, o, lse, causal, softmax_scale, dq, dk, dv) -> bool:
+    """Variable-length backward in one launch per kernel over the padded batch (fa2_sm100_bwd_varlen): the deterministic
+    spilled-dS path (or dK / dV alone when dq is None). Returns False - the caller then falls back to one call per
+    sequence - when the dS workspace of the padded shape does not fit. dq / dk / dv arrive zero-filled."""
+    batch, seqlen, nheads_q, head_dim = q.shape
+    nheads_kv = k.shape[2]
+    seqlen_rounded = math.ceil(seqlen / 128) * 128
+    scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
+    assert nheads_q % nheads_kv == 0, f"{nheads_q = } is not divisible by {nheads_kv =}"
+    assert lse.shape == (batch, nheads_q, seqlen_rounded) and lse.dtype == torch.float32 and lse.is_contiguous()
+    assert dO.shape == q.shape and o.shape == q.shape and k.shape == v.shape
+    assert q.is_cuda and k.is_cuda and v.is_cuda and o.is_cuda and dO.is_cuda and lse.is_cuda and attention_mask.is_cuda
+    assert q.dtype == k.dtype == v.dtype == o.dtype == dO.dtype, "All tensors must have the same type"
+    assert q.stride(-1) == k.stride(-1) == v.stride(-1) == o.stride(-1) == 1
+    lib = _lib.load()
+    dt = encode_dtype(q)
+    mode = _lib.DQ_DET_SPILL if dq is not None else _lib.DQ_NONE
+    ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(batch, nheads_q, seqlen, seqlen, head_dim, int(bool(causal)), mode)
+    if ws_bytes > _spill_limit_bytes():
+        return False
+    with torch.cuda.device(q.device):
+        try:
+            workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+        except torch.OutOfMemoryError:
+            return False
+        stream = _stream_ptr(q.device)
+        seqlens = device_sequence_lengths(attention_mask)
+        tmap_ws = torch.empty(lib.fa2_sm100_varlen_workspace_bytes(batch), device=q.device, dtype=torch.uint8)
+        delta = torch.empty_like(lse)
+        # dK / dV are always produced by the kernel pair; a caller that only wants dQ gets scratch ones
+        dk_ = dk if dk is not None else torch.zeros_like(k)
+        dv_ = dv if dv is not None else torch.zeros_like(v)
+        code = lib.fa2_sm100_bwd_delta_varlen(
+            o.data_ptr(), dO.data_ptr(), delta.data_ptr(), batch, nheads_q, seqlen, head_dim,
+            _lib.strides3(o), _lib.strides3(dO), seqlen_rounded, dt, seqlens.data_ptr(), stream)
+        _lib.check(code, "fa2_sm100_bwd_delta_varlen")
+        code = lib.fa2_sm100_bwd_varlen(
+            dO.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+            dq.data_ptr() if dq is not None else None, dk_.data_ptr(), dv_.data_ptr(), workspace.data_ptr(), ws_bytes,
+            batch, nheads_q, nheads_kv, seqlen, head_dim,
+            _lib.strides3(dO), _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
+            _lib.strides3(dq if dq is not None else q), _lib.strides3(dk_), _lib.strides3(dv_),
+            seqlen_rounded, scale, int(bool(causal)), mode, dt, encode_dtype(dq) if dq is not None else dt,
+            seqlens.data_ptr(), tmap_ws.data_ptr(), tmap_ws.numel(), stream)
+        _lib.check(code, "fa2_sm100_bwd_varlen")
+    return True
 
 
 def _flash_attn_backward(
@@ -78,6 +126,12 @@ def _flash_attn_backward(
         dq = torch.zeros_like(q, dtype=torch.float32 if dq_dtype is None else dq_dtype) if need_dq else None
         dk = torch.zeros_like(k) if need_dkdv else None
         dv = torch.zeros_like(v) if need_dkdv else None
+        if not need_dq and not need_dkdv:
+            return None, None, None
+        if varlen_in_kernel(q, k, v):
+            done = _backward_varlen(dO, q, k, v, attention_mask, o, lse, causal, softmax_scale, dq, dk, dv)
+            if done:
+                return dq, dk, dv
         for b, n in enumerate(sequence_lengths(attention_mask)):
             if n == 0:
                 continue

@@ -87,6 +87,32 @@ int check_common(int B, int Hq, int Hkv, int Sq, int Sk, int D, int dtype) {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// variable-length mode: per-sequence copies of the launch's tensor maps, built on the device (varlen_sm100.cu)
+struct VarlenTensor { const CUtensorMap* map; const void* ptr; int64_t batch_stride_elems; };
+
+int setup_varlen_maps(const VarlenTensor* tensors, int n, const int32_t* seqlens_dev, void* tmap_ws, size_t tmap_ws_bytes,
+                      int B, int S, cudaStream_t st) {
+  if (!seqlens_dev || !tmap_ws) return fail(FA2_E_NULL_POINTER, "seqlens / tensor-map workspace: null pointer");
+  if (tmap_ws_bytes < fa2_sm100_varlen_workspace_bytes(B))
+    return fail(FA2_E_WORKSPACE_TOO_SMALL, "tensor-map workspace has %zu bytes, %zu needed", tmap_ws_bytes,
+                fa2_sm100_varlen_workspace_bytes(B));
+  if (reinterpret_cast<uintptr_t>(tmap_ws) % 128) return fail(FA2_E_BAD_ALIGNMENT, "tensor-map workspace not 128-byte aligned");
+  CUtensorMap templates[6];
+  fa2::VarlenSetupParams sp{};
+  sp.seqlens = seqlens_dev;
+  sp.out = static_cast<CUtensorMap*>(tmap_ws);
+  sp.n_maps = n;
+  sp.S = S;
+  for (int i = 0; i < n; ++i) {
+    templates[i] = *tensors[i].map;
+    sp.base[i] = reinterpret_cast<uint64_t>(tensors[i].ptr);
+    sp.batch_stride_bytes[i] = static_cast<uint64_t>(tensors[i].batch_stride_elems) * 2u;
+  }
+  cudaError_t ce = fa2::launch_varlen_maps(templates, sp, B, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_varlen_maps_kernel launch");
+  return 0;
+}
+
 // bias: [1 | B, 1 | Hq, Sq, Sk] with (batch, head, row) element strides; a broadcast dimension carries stride 0
 int make_bias_view(fa2::BiasView* view, const void* bias, int bias_dtype, const int64_t bias_strides[3], int dtype) {
   *view = fa2::BiasView{};
@@ -112,9 +138,30 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // tensor maps carry the real head dim, so TMA zero-fills the missing columns on load and clips them on store.
 int kernel_head_dim(int D) { return D <= 64 ? 64 : 128; }
 
+int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int Sq,
+             int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+             const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
+             const void* bias, int bias_dtype, const int64_t bias_strides[3], float dropout_p,
+             uint64_t dropout_seed, const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes, void* stream);
+int bwd_impl(const void* dout, const void* q, const void* k, const void* v, const float* lse,
+             const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+             int Hq, int Hkv, int Sq, int Sk, int D, const int64_t do_strides[3], const int64_t q_strides[3],
+             const int64_t k_strides[3], const int64_t v_strides[3], const int64_t dq_strides[3],
+             const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride,
+             float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype, const void* bias,
+             int bias_dtype, const int64_t bias_strides[3], const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes,
+             void* stream);
+int delta_impl(const void* o, const void* dout, float* delta, int B, int Hq, int Sq, int D,
+               const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride, int dtype,
+               void* workspace, size_t workspace_bytes, const int32_t* seqlens, void* stream);
+
 }  // namespace
 
 extern "C" {
+
+size_t fa2_sm100_varlen_workspace_bytes(int B) {
+  return B < 1 ? 0 : static_cast<size_t>(B) * fa2::kVarlenMapsPerBatch * sizeof(CUtensorMap);
+}
 
 int fa2_sm100_version(void) { return FA2_SM100_ABI_VERSION; }
 
@@ -133,6 +180,30 @@ int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, floa
                       const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
                       const void* bias, int bias_dtype, const int64_t bias_strides[3], float dropout_p,
                       uint64_t dropout_seed, void* stream) {
+  return fwd_impl(q, k, v, o, lse, B, Hq, Hkv, Sq, Sk, D, q_strides, k_strides, v_strides, o_strides, lse_row_stride,
+                  softmax_scale, causal, dtype, bias, bias_dtype, bias_strides, dropout_p, dropout_seed, nullptr, nullptr,
+                  0, stream);
+}
+
+int fa2_sm100_fwd_varlen(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int S,
+                         int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                         const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
+                         const int32_t* seqlens, void* tmap_workspace, size_t tmap_workspace_bytes, void* stream) {
+  if (!seqlens) return fail(FA2_E_NULL_POINTER, "seqlens: null pointer");
+  return fwd_impl(q, k, v, o, lse, B, Hq, Hkv, S, S, D, q_strides, k_strides, v_strides, o_strides, lse_row_stride,
+                  softmax_scale, causal, dtype, nullptr, 0, nullptr, 0.f, 0ull, seqlens, tmap_workspace,
+                  tmap_workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int Sq,
+             int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+             const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
+             const void* bias, int bias_dtype, const int64_t bias_strides[3], float dropout_p,
+             uint64_t dropout_seed, const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes, void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
   if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(FA2_E_BAD_SHAPE, "dropout_p must be in [0, 1)");
   if (!lse) return fail(FA2_E_NULL_POINTER, "lse: null pointer");
@@ -156,14 +227,42 @@ int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, floa
   p.inv_keep = 1.0f / (1.0f - dropout_p);
   p.seed_lo = static_cast<uint32_t>(dropout_seed & 0xffffffffull);
   p.seed_hi = static_cast<uint32_t>(dropout_seed >> 32);
+  if (seqlens) {
+    const VarlenTensor vt[4] = {{&tq, q, q_strides[0]}, {&tk, k, k_strides[0]}, {&tv, v, v_strides[0]}, {&to, o, o_strides[0]}};
+    if (int e = setup_varlen_maps(vt, 4, seqlens, tmap_ws, tmap_ws_bytes, B, Sq, static_cast<cudaStream_t>(stream))) return e;
+    p.seqlens = seqlens;
+    p.vmaps = static_cast<const CUtensorMap*>(tmap_ws);
+  }
   cudaError_t ce = fa2::launch_fwd(kernel_head_dim(D), dtype == FA2_DTYPE_BF16, tq, tk, tv, to, p, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_fwd launch");
   return 0;
 }
 
+}  // namespace
+
+extern "C" {
+
 int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, int Hq, int Sq, int D,
                         const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride, int dtype,
                         void* workspace, size_t workspace_bytes, void* stream) {
+  return delta_impl(o, dout, delta, B, Hq, Sq, D, o_strides, do_strides, lse_row_stride, dtype, workspace, workspace_bytes,
+                    nullptr, stream);
+}
+
+int fa2_sm100_bwd_delta_varlen(const void* o, const void* dout, float* delta, int B, int Hq, int S, int D,
+                               const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride, int dtype,
+                               const int32_t* seqlens, void* stream) {
+  if (!seqlens) return fail(FA2_E_NULL_POINTER, "seqlens: null pointer");
+  return delta_impl(o, dout, delta, B, Hq, S, D, o_strides, do_strides, lse_row_stride, dtype, nullptr, 0, seqlens, stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+int delta_impl(const void* o, const void* dout, float* delta, int B, int Hq, int Sq, int D,
+               const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride, int dtype,
+               void* workspace, size_t workspace_bytes, const int32_t* seqlens, void* stream) {
   if (int e = check_common(B, Hq, Hq, Sq, 1, D, dtype)) return e;
   if (!o || !dout || !delta) return fail(FA2_E_NULL_POINTER, "o / dout / delta: null pointer");
   if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
@@ -187,10 +286,15 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta, int B, in
     p.dq_sem = reinterpret_cast<int*>(static_cast<char*>(workspace) +
                                       static_cast<size_t>(B) * Hq * lse_row_stride * D * sizeof(float));
   }
+  p.seqlens = seqlens;
   cudaError_t ce = fa2::launch_delta(dtype == FA2_DTYPE_BF16, p, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd_delta launch");
   return 0;
 }
+
+}  // namespace
+
+extern "C" {
 
 int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq, int D, const int64_t dq_strides[3],
                          float softmax_scale, int out_dtype, void* stream);
@@ -230,6 +334,39 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
                       const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride,
                       float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype, const void* bias,
                       int bias_dtype, const int64_t bias_strides[3], void* stream) {
+  return bwd_impl(dout, q, k, v, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, Hq, Hkv, Sq, Sk, D, do_strides,
+                  q_strides, k_strides, v_strides, dq_strides, dk_strides, dv_strides, lse_row_stride, softmax_scale, causal,
+                  deterministic, dtype, dq_dtype, bias, bias_dtype, bias_strides, nullptr, nullptr, 0, stream);
+}
+
+int fa2_sm100_bwd_varlen(const void* dout, const void* q, const void* k, const void* v, const float* lse,
+                         const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+                         int Hq, int Hkv, int S, int D, const int64_t do_strides[3], const int64_t q_strides[3],
+                         const int64_t k_strides[3], const int64_t v_strides[3], const int64_t dq_strides[3],
+                         const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride,
+                         float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype,
+                         const int32_t* seqlens, void* tmap_workspace, size_t tmap_workspace_bytes, void* stream) {
+  if (!seqlens) return fail(FA2_E_NULL_POINTER, "seqlens: null pointer");
+  if (deterministic != FA2_DQ_DET_SPILL && deterministic != FA2_DQ_NONE && deterministic != FA2_DQ_SPILL_DKDV)
+    return fail(FA2_E_BAD_SHAPE, "variable-length mode: `deterministic` must be 5 (FA2_DQ_DET_SPILL), 3 (FA2_DQ_NONE) or 6");
+  if (!dk || !dv) return fail(FA2_E_NULL_POINTER, "dk / dv: null pointer");
+  return bwd_impl(dout, q, k, v, lse, delta, dq, dk, dv, workspace, workspace_bytes, B, Hq, Hkv, S, S, D, do_strides,
+                  q_strides, k_strides, v_strides, dq_strides, dk_strides, dv_strides, lse_row_stride, softmax_scale, causal,
+                  deterministic, dtype, dq_dtype, nullptr, 0, nullptr, seqlens, tmap_workspace, tmap_workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+int bwd_impl(const void* dout, const void* q, const void* k, const void* v, const float* lse,
+             const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
+             int Hq, int Hkv, int Sq, int Sk, int D, const int64_t do_strides[3], const int64_t q_strides[3],
+             const int64_t k_strides[3], const int64_t v_strides[3], const int64_t dq_strides[3],
+             const int64_t dk_strides[3], const int64_t dv_strides[3], int64_t lse_row_stride,
+             float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype, const void* bias,
+             int bias_dtype, const int64_t bias_strides[3], const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes,
+             void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
   fa2::BiasView bias_view{};
   if (int e = make_bias_view(&bias_view, bias, bias_dtype, bias_strides, dtype)) return e;
@@ -272,6 +409,12 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
   }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (seqlens) {
+    const VarlenTensor vt[6] = {{&tq, q, q_strides[0]}, {&tk, k, k_strides[0]}, {&tv, v, v_strides[0]},
+                                {&tdo, dout, do_strides[0]}, {&tdk, dk, dk_strides[0]}, {&tdv, dv, dv_strides[0]}};
+    if (int e = setup_varlen_maps(vt, 6, seqlens, tmap_ws, tmap_ws_bytes, B, Sq, st)) return e;
+  }
+  const CUtensorMap* vmaps = seqlens ? static_cast<const CUtensorMap*>(tmap_ws) : nullptr;
   const int sq_pad = round_up(Sq, 128);
   const bool fused = deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED;
   fa2::BwdParams p{};
@@ -320,7 +463,9 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
       k.max_ctas = dkdv_ctas;  // experiments only (scripts/concurrent_probe.py): cap on the persistent grid
       for (int i = 0; i < 3; ++i) { k.dk_strides[i] = dk_strides[i]; k.dv_strides[i] = dv_strides[i]; }
       k.bias = bias_view;
-      if (nonpersistent || bias || D != Dk) ce = fa2::launch_bwd_dkdv(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
+      k.seqlens = seqlens;
+      k.vmaps = vmaps;
+      if (nonpersistent || bias || seqlens || D != Dk) ce = fa2::launch_bwd_dkdv(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
       else ce = fa2::launch_bwd_dkdv_persistent(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
@@ -345,6 +490,8 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
     static const int dq_ctas = [] { const char* e = getenv("FA2_SM100_DQ_CTAS"); return e ? atoi(e) : 0; }();
     d.max_ctas = dq_ctas;  // experiments only: cap on the persistent grid
     d.d_actual = D;
+    d.seqlens = seqlens;
+    d.vmaps = vmaps;
     ce = fa2::launch_bwd_dq_spill(Dk, dtype == FA2_DTYPE_BF16, tk, d, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ (spill) launch");
     return 0;
@@ -368,6 +515,10 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
   if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ launch");
   return 0;
 }
+
+}  // namespace
+
+extern "C" {
 
 int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq, int D, const int64_t dq_strides[3],
                          float softmax_scale, int out_dtype, void* stream) {

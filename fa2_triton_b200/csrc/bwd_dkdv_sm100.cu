@@ -144,13 +144,22 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int n_q_blocks = (p.Sq + kBlk - 1) / kBlk;
   const int nblk = static_cast<int>(blockIdx.x);  // causal: low key blocks are seen by the most query blocks - longest first
   const int head_kv = blockIdx.y;
   const int batch = blockIdx.z;
-  const int group = p.Hq / p.Hkv;
-  const int shift = p.Sk - p.Sq;
   const int kv0 = nblk * kBlk;
+  // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
+  int Sq = p.Sq, Sk = p.Sk, bc = batch;
+  const CUtensorMap *mq = &tmap_q, *mk = &tmap_k, *mv = &tmap_v, *mdo = &tmap_do, *mdk = &tmap_dk, *mdv = &tmap_dv;
+  if (p.seqlens != nullptr) {
+    Sq = Sk = p.seqlens[batch];
+    const CUtensorMap* m = p.vmaps + static_cast<size_t>(batch) * kVarlenMapsPerBatch;
+    mq = m; mk = m + 1; mv = m + 2; mdo = m + 3; mdk = m + 4; mdv = m + 5; bc = 0;
+    if (kv0 >= Sk) return;  // key block in the padding: its dK / dV rows were zero-filled by the caller
+  }
+  const int n_q_blocks = (Sq + kBlk - 1) / kBlk;
+  const int group = p.Hq / p.Hkv;
+  const int shift = Sk - Sq;
 
   // first query block that sees this key block (bottom-right aligned causal mask)
   int m_start = 0;
@@ -161,12 +170,20 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    tma_prefetch_desc(&tmap_do);
-    tma_prefetch_desc(&tmap_dk);
-    tma_prefetch_desc(&tmap_dv);
+    if (p.seqlens != nullptr) {  // maps published by fa2_varlen_maps_kernel
+      tmap_acquire(mq);
+      tmap_acquire(mk);
+      tmap_acquire(mv);
+      tmap_acquire(mdo);
+    }
+    tma_prefetch_desc(mq);
+    tma_prefetch_desc(mk);
+    tma_prefetch_desc(mv);
+    tma_prefetch_desc(mdo);
+    if (p.seqlens == nullptr) {
+      tma_prefetch_desc(mdk);
+      tma_prefetch_desc(mdv);
+    }
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -203,8 +220,8 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (T > 0 && elect_one()) {
         mbar_arrive_expect_tx(&bars[kKvFull], 2 * L::kTileBytes);
         for (int j = 0; j < kSub; ++j) {
-          tma_load_4d(sK + j * kSubBytes, &tmap_k, &bars[kKvFull], j * 64, kv0, head_kv, batch);
-          tma_load_4d(sV + j * kSubBytes, &tmap_v, &bars[kKvFull], j * 64, kv0, head_kv, batch);
+          tma_load_4d(sK + j * kSubBytes, mk, &bars[kKvFull], j * 64, kv0, head_kv, bc);
+          tma_load_4d(sV + j * kSubBytes, mv, &bars[kKvFull], j * 64, kv0, head_kv, bc);
         }
         for (int it = 0; it < T; ++it) {
           const int qs = it % kQStages, ds = it % kDoStages;
@@ -216,14 +233,14 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           mbar_wait(&bars[kQEmpty + qs], qph ^ 1);
           mbar_arrive_expect_tx(&bars[kQFull + qs], L::kTileBytes + kBlk * 4);
           for (int j = 0; j < kSub; ++j)
-            tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, &tmap_q, &bars[kQFull + qs], j * 64, m * kBlk, head, batch);
+            tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, mq, &bars[kQFull + qs], j * 64, m * kBlk, head, bc);
           bulk_load_1d(sLse + qs * kBlk, p.lse + row_off, kBlk * 4, &bars[kQFull + qs]);
           // dO(it) + its delta row: released by dV(it - 2) and by the readers of delta(it - 2)
           mbar_wait(&bars[kDoEmpty + ds], dph ^ 1);
           mbar_wait(&bars[kDeltaEmpty + ds], dph ^ 1);
           mbar_arrive_expect_tx(&bars[kDoFull + ds], L::kTileBytes + kBlk * 4);
           for (int j = 0; j < kSub; ++j)
-            tma_load_4d(sDO + ds * L::kTileBytes + j * kSubBytes, &tmap_do, &bars[kDoFull + ds], j * 64, m * kBlk, head, batch);
+            tma_load_4d(sDO + ds * L::kTileBytes + j * kSubBytes, mdo, &bars[kDoFull + ds], j * 64, m * kBlk, head, bc);
           bulk_load_1d(sDelta + ds * kBlk, p.delta + row_off, kBlk * 4, &bars[kDoFull + ds]);
         }
       }
@@ -346,7 +363,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int q0 = m * kBlk + wg * kCmpCols;  // first query column of this thread's slice
       const float4* lse_s = reinterpret_cast<const float4*>(sLse + qs * kBlk + wg * kCmpCols);
       const float4* delta_s = reinterpret_cast<const float4*>(sDelta + ds * kBlk + wg * kCmpCols);
-      const bool need_mask = (kv0 + kBlk > p.Sk) || (m * kBlk + kBlk > p.Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
+      const bool need_mask = (kv0 + kBlk > Sk) || (m * kBlk + kBlk > Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
       // kBias: this thread's 32 bias values bias[q0 + j][kv] (one coalesced 64-byte warp load per query row), fetched
       // before the waits below so that their latency hides behind the S^T product; scaled to the log2 domain.
       // 16-bit values travel as packed pairs, fp32 ones unpacked.
@@ -354,18 +371,18 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if constexpr (kBias) {
         const int64_t off0 = batch * p.bias.sb + (head_kv * group + it / m_count) * p.bias.sh +
                              static_cast<int64_t>(q0) * p.bias.sm + kv;
-        const bool col_ok = kv < p.Sk;
+        const bool col_ok = kv < Sk;
         if (p.bias.is_fp32) {
           const float* bp = static_cast<const float*>(p.bias.ptr) + off0;
 #pragma unroll
           for (int j = 0; j < kCmpCols; ++j)
-            braw[j] = (col_ok && q0 + j < p.Sq) ? __float_as_uint(__ldg(bp + j * p.bias.sm)) : 0u;
+            braw[j] = (col_ok && q0 + j < Sq) ? __float_as_uint(__ldg(bp + j * p.bias.sm)) : 0u;
         } else {
           const uint16_t* bp = static_cast<const uint16_t*>(p.bias.ptr) + off0;
 #pragma unroll
           for (int j = 0; j < kCmpCols; j += 2) {
-            const uint32_t lo = (col_ok && q0 + j < p.Sq) ? __ldg(bp + j * p.bias.sm) : 0u;
-            const uint32_t hi = (col_ok && q0 + j + 1 < p.Sq) ? __ldg(bp + (j + 1) * p.bias.sm) : 0u;
+            const uint32_t lo = (col_ok && q0 + j < Sq) ? __ldg(bp + j * p.bias.sm) : 0u;
+            const uint32_t hi = (col_ok && q0 + j + 1 < Sq) ? __ldg(bp + (j + 1) * p.bias.sm) : 0u;
             braw[j / 2] = lo | (hi << 16);
           }
         }
@@ -416,9 +433,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
         for (int j = 0; j < kPairs; ++j) {
           const int qi = q0 + 2 * j;
-          const bool row_ok = kv < p.Sk;
-          const bool ok0 = row_ok && (qi < p.Sq) && (!p.causal || kv <= qi + shift);
-          const bool ok1 = row_ok && (qi + 1 < p.Sq) && (!p.causal || kv <= qi + 1 + shift);
+          const bool row_ok = kv < Sk;
+          const bool ok0 = row_ok && (qi < Sq) && (!p.causal || kv <= qi + shift);
+          const bool ok1 = row_ok && (qi + 1 < Sq) && (!p.causal || kv <= qi + 1 + shift);
           pf[j].x = ok0 ? pf[j].x : 0.f;
           pf[j].y = ok1 ? pf[j].y : 0.f;
         }
@@ -527,9 +544,13 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     fence_proxy_async_smem();
     named_bar_sync(1, kCmpThreads);
     if (threadIdx.x == 0) {
+      if (p.seqlens != nullptr) {
+        tmap_acquire(mdk);
+        tmap_acquire(mdv);
+      }
       for (int j = 0; j < kSub; ++j) {
-        tma_store_4d(&tmap_dk, sK + j * kSubBytes, j * 64, kv0, head_kv, batch);
-        tma_store_4d(&tmap_dv, sV + j * kSubBytes, j * 64, kv0, head_kv, batch);
+        tma_store_4d(mdk, sK + j * kSubBytes, j * 64, kv0, head_kv, bc);
+        tma_store_4d(mdv, sV + j * kSubBytes, j * 64, kv0, head_kv, bc);
       }
       bulk_commit_group();
       bulk_wait_group_read<0>();

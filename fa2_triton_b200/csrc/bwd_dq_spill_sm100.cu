@@ -124,9 +124,15 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
         if (w >= n_items) break;
         const Item it = item_of(w, n_q_blocks, p.Hq);
         const int head_kv = it.head / group;
-        const int nblk = visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
+        const int len = p.seqlens != nullptr ? p.seqlens[it.batch] : 0;  // variable-length mode: this sequence's length
+        const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
+                                              : visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
         const long long tile0 = (static_cast<long long>(it.batch) * p.Hq + it.head) * p.tiles_per_head +
                                 ds_tile_prefix(it.m, p.Sq, p.Sk, p.causal);
+        // variable-length mode: the K map of this batch element (bounded by its length; batch coordinate 0)
+        const CUtensorMap* mk = p.seqlens != nullptr ? p.vmaps + static_cast<size_t>(it.batch) * kVarlenMapsPerBatch + 1 : &tmap_k;
+        const int bc = p.seqlens != nullptr ? 0 : it.batch;
+        if (p.seqlens != nullptr) tmap_acquire(mk);
         for (int i = 0; i < nblk; ++i, ++c) {
           const uint32_t s = c % kStages;
           uint8_t* stage = smem + s * L::kStageBytes;
@@ -134,7 +140,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
           mbar_arrive_expect_tx(&full[s], L::kStageBytes);
           bulk_load_1d_hint(stage, base + (tile0 + i) * kDsTileBytes, kDsTileBytes, &full[s], policy);
           for (int j = 0; j < kSub; ++j)
-            tma_load_4d(stage + kDsTileBytes + j * kSubBytes, &tmap_k, &full[s], j * 64, i * kBlk, head_kv, it.batch);
+            tma_load_4d(stage + kDsTileBytes + j * kSubBytes, mk, &full[s], j * 64, i * kBlk, head_kv, bc);
         }
       }
     }
@@ -151,7 +157,9 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
         mbar_arrive(&item_empty[slot]);
         if (w < 0) break;
         const Item it = item_of(w, n_q_blocks, p.Hq);
-        const int nblk = visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
+        const int len = p.seqlens != nullptr ? p.seqlens[it.batch] : 0;  // variable-length mode: this sequence's length
+        const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
+                                              : visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
         const uint32_t buf = t & 1;
         const uint32_t acc = buf * 256;
         mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);  // the epilogue of item t - 2 has read this accumulator
@@ -186,7 +194,9 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
       if (w < 0) break;
       const Item it = item_of(w, n_q_blocks, p.Hq);
       const int row = it.m * kBlk + r;
-      const int nblk = visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
+      const int len = p.seqlens != nullptr ? p.seqlens[it.batch] : 0;  // variable-length mode: this sequence's length
+        const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
+                                              : visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
       const uint32_t buf = t & 1;
       mbar_wait(&acc_full[buf], (t >> 1) & 1);
       tcgen05_fence_after();
@@ -205,7 +215,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
           tcgen05_fence_before();
           mbar_arrive(&acc_empty[buf]);
         }
-        if (row < p.Sq) {
+        if (row < (p.seqlens != nullptr ? len : p.Sq)) {
           const int64_t off = off0 + chunk * 32;
           if (p.dq_is_16bit) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dq) + off);

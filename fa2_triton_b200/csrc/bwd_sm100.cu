@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
   constexpr int kPasses = 4;  // rows per thread: all 2 x kPasses 16-byte loads are issued before the first use
   constexpr int kRowsPerBlock = kRowsPerPass * kPasses;
   const int head = blockIdx.y, batch = blockIdx.z;
+  const int sq_valid = p.seqlens != nullptr ? p.seqlens[batch] : p.Sq;  // variable-length mode: this sequence's rows
   const int row0 = blockIdx.x * kRowsPerBlock + threadIdx.x / kThreadsPerRow;
   const int part = threadIdx.x % kThreadsPerRow;
   const uint16_t* obase = reinterpret_cast<const uint16_t*>(p.o) + batch * p.o_strides[0] + head * p.o_strides[1] + part * 8;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
   for (int i = 0; i < kPasses; ++i) {
     const int row = row0 + i * kRowsPerPass;
     ov[i] = gv[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < p.Sq && part * 8 < p.D) {  // p.D < D: the tensors' head dim is zero-padded up to the kernel's
+    if (row < sq_valid && part * 8 < p.D) {  // p.D < D: the tensors' head dim is zero-padded up to the kernel's
       ov[i] = *reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(row) * p.o_strides[2]);
       gv[i] = *reinterpret_cast<const uint4*>(gbase + static_cast<int64_t>(row) * p.do_strides[2]);
     }

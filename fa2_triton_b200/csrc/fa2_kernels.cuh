@@ -12,6 +12,24 @@ namespace fa2 {
 // ---------------------------------------------------------------------------------------------
 // forward (fwd_sm100.cu)
 // ---------------------------------------------------------------------------------------------
+// Variable-length batches (right-padded [B, S, ...] tensors, one length per batch element; query and key lengths
+// coincide like in the reference's attention_mask mode, src/forward/caller.py:25-28): `seqlens` (device, [B]) gives the
+// lengths and `vmaps` (device) per-batch tensor maps bounded by them - [B][kVarlenMapsPerBatch], order q, k, v, o for the
+// forward and q, k, v, dO, dK, dV for the backward - so that TMA zero-fills / clips at each sequence's own end and
+// nothing stored in the padding can reach a result. Both nullptr outside that mode.
+constexpr int kVarlenMapsPerBatch = 8;
+
+// setup kernel (varlen_sm100.cu): templates[i] is the launch's full map of tensor i, out[b][i] its per-sequence copy
+struct VarlenSetupParams {
+  const int* seqlens;            // device, [B]
+  CUtensorMap* out;              // device, [B][kVarlenMapsPerBatch], 128-byte aligned
+  uint64_t base[6];              // device address of tensor i
+  uint64_t batch_stride_bytes[6];
+  int n_maps;                    // <= 6
+  int S;                         // padded sequence length: lengths are clamped to [0, S]
+};
+cudaError_t launch_varlen_maps(const CUtensorMap* templates, const VarlenSetupParams& p, int B, cudaStream_t stream);
+
 struct FwdParams {
   float* lse;        // [B, Hq, lse_stride] fp32, log2 domain
   int B, Hq, Hkv, Sq, Sk;
@@ -25,6 +43,8 @@ struct FwdParams {
   float dropout_p;      // 0: no dropout
   float inv_keep;       // 1 / (1 - dropout_p)
   uint32_t seed_lo, seed_hi;
+  const int* seqlens;         // variable-length mode (see above), else nullptr
+  const CUtensorMap* vmaps;
 };
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -43,6 +63,7 @@ struct DeltaParams {
   int64_t do_strides[3];
   float* dq_accum;  // optional: backward workspace to clear ([B, Hq, lse_stride, D] fp32), or nullptr
   int* dq_sem;      // optional: [B, Hq, lse_stride / 128] tickets to clear, or nullptr
+  const int* seqlens;  // variable-length mode: rows at or beyond a sequence's length get delta = 0 unread
 };
 cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream);
 
@@ -131,6 +152,8 @@ struct DkdvParams {
   int64_t dv_strides[3];
   int max_ctas;           // > 0: cap on the persistent grid (the rest of the SMs is left to a concurrent kernel)
   BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
+  const int* seqlens;     // variable-length mode (one CTA per key block only), else nullptr
+  const CUtensorMap* vmaps;
 };
 cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                                        const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,
@@ -152,6 +175,8 @@ struct DqSpillParams {
   int causal;
   int max_ctas;        // > 0: cap on the persistent grid
   int d_actual;        // head dim of the tensors (multiple of 8, <= the kernel's D): columns beyond it are not stored
+  const int* seqlens;  // variable-length mode, else nullptr
+  const CUtensorMap* vmaps;
 };
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream);
 

@@ -162,16 +162,30 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int batch = blockIdx.z;
   const int head_kv = head / (p.Hq / p.Hkv);
   const int row0 = pair * 2 * kBM;
+  // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
+  int Sq = p.Sq, Sk = p.Sk, bc = batch;
+  const CUtensorMap *mq = &tmap_q, *mk = &tmap_k, *mv = &tmap_v, *mo = &tmap_o;
+  if (p.seqlens != nullptr) {
+    Sq = Sk = p.seqlens[batch];
+    const CUtensorMap* m = p.vmaps + static_cast<size_t>(batch) * kVarlenMapsPerBatch;
+    mq = m; mk = m + 1; mv = m + 2; mo = m + 3; bc = 0;
+    if (row0 >= Sq) return;  // tile pair in the padding: its rows of O and LSE were zero-filled by the caller
+  }
 
-  const int nblk0 = num_kv_blocks(row0, p.Sq, p.Sk, p.causal);
-  const int nblk1 = num_kv_blocks(row0 + kBM, p.Sq, p.Sk, p.causal);
+  const int nblk0 = num_kv_blocks(row0, Sq, Sk, p.causal);
+  const int nblk1 = num_kv_blocks(row0 + kBM, Sq, Sk, p.causal);
   const int nblk_max = max(nblk0, nblk1);
 
   if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    tma_prefetch_desc(&tmap_o);
+    if (p.seqlens != nullptr) {  // maps published by fa2_varlen_maps_kernel
+      tmap_acquire(mq);
+      tmap_acquire(mk);
+      tmap_acquire(mv);
+    }
+    tma_prefetch_desc(mq);
+    tma_prefetch_desc(mk);
+    tma_prefetch_desc(mv);
+    if (p.seqlens == nullptr) tma_prefetch_desc(mo);
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -208,22 +222,22 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp == kTmaWarp) {
     // ======================================= TMA producer =======================================
     if (nblk_max > 0 && elect_one()) {
-      const int n_q_tiles = (row0 + kBM < p.Sq) ? 2 : 1;
+      const int n_q_tiles = (row0 + kBM < Sq) ? 2 : 1;
       mbar_arrive_expect_tx(q_full, n_q_tiles * L::kTileBytes);
       for (int t = 0; t < n_q_tiles; ++t)
         for (int j = 0; j < kSub; ++j)
-          tma_load_4d(sQ + t * L::kTileBytes + j * kSubBytes, &tmap_q, q_full, j * 64, row0 + t * kBM, head, batch);
+          tma_load_4d(sQ + t * L::kTileBytes + j * kSubBytes, mq, q_full, j * 64, row0 + t * kBM, head, bc);
       for (int i = 0; i < nblk_max; ++i) {
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], L::kTileBytes);
         for (int j = 0; j < kSub; ++j)
-          tma_load_4d(sK + s * L::kTileBytes + j * kSubBytes, &tmap_k, &k_full[s], j * 64, i * kBN, head_kv, batch);
+          tma_load_4d(sK + s * L::kTileBytes + j * kSubBytes, mk, &k_full[s], j * 64, i * kBN, head_kv, bc);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], L::kTileBytes);
         for (int j = 0; j < kSub; ++j)
-          tma_load_4d(sV + s * L::kTileBytes + j * kSubBytes, &tmap_v, &v_full[s], j * 64, i * kBN, head_kv, batch);
+          tma_load_4d(sV + s * L::kTileBytes + j * kSubBytes, mv, &v_full[s], j * 64, i * kBN, head_kv, bc);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -323,7 +337,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     constexpr int kOCols = D / kHalves;                                 // columns of O this thread rescales / stores
     const uint32_t tO = tmem_base + lane_sel + 256 + t * D + half * kOCols;
     const float c = p.scale_log2;
-    const int shift = p.Sk - p.Sq;
+    const int shift = Sk - Sq;
     auto xchg_slot = [&](int par, int h, int kind = 0) { return xchg + (((par * 2 + kind) * 2 + t) * 2 + h) * kBM + r; };
 
     float m_ref = -INFINITY;
@@ -360,7 +374,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int64_t head_off = batch * p.bias.sb + head * p.bias.sh;
         const int gc0 = bias_col0 + group * 4 * kChunkCols;
         // whole pieces in bounds and 16-byte aligned for every row of the warp (warp-uniform)
-        bias_fast = (wrow0 + 32 <= p.Sq) && (bias_col0 + kBN <= p.Sk) && ((p.bias.sm * kElem) % 16 == 0) &&
+        bias_fast = (wrow0 + 32 <= Sq) && (bias_col0 + kBN <= Sk) && ((p.bias.sm * kElem) % 16 == 0) &&
                     ((reinterpret_cast<uintptr_t>(base) + (head_off + bias_col0) * kElem) % 16 == 0);
 #pragma unroll
         for (int li = 0; li < 16; ++li) {
@@ -374,7 +388,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int e = 0; e < kPer16; ++e) {
-              const bool ok = grow < p.Sq && gcol + e < p.Sk;
+              const bool ok = grow < Sq && gcol + e < Sk;
               if constexpr (kElem == 4) w[e] = ok ? __ldg(reinterpret_cast<const uint32_t*>(base) + idx + e) : 0u;
               else w[e / 2] |= (ok ? static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t*>(base) + idx + e)) : 0u) << (16 * (e % 2));
             }
@@ -477,9 +491,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
       const int col0 = i * kBN + half * kCols;
       const int block_last = i * kBN + kBN - 1;
-      const bool need_mask = (block_last >= p.Sk) || (p.causal && block_last > tile_row0 + shift);
+      const bool need_mask = (block_last >= Sk) || (p.causal && block_last > tile_row0 + shift);
       if (need_mask) {
-        const int limit = p.causal ? min(p.Sk - 1, row + shift) : (p.Sk - 1);
+        const int limit = p.causal ? min(Sk - 1, row + shift) : (Sk - 1);
 #pragma unroll
         for (int j = 0; j < kCols; ++j) s[j] = (col0 + j <= limit) ? s[j] : -INFINITY;
       }
@@ -648,7 +662,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
 
     // ------------------------------ epilogue: O / l -> smem -> TMA store ---------------------------
-    if (tile_row0 < p.Sq) {
+    if (tile_row0 < Sq) {
       if constexpr (kHalves == 2) {
         // full row sum = the two partial sums (both relative to the same m_ref); slots of parity nblk & 1 are free:
         // the last block used parity (nblk - 1) & 1 and every thread has passed that block's barrier
@@ -695,7 +709,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       fence_proxy_async_smem();
       named_bar_sync(1 + t, kTileSmxThreads);
       if (r == 0 && half == 0) {
-        for (int j = 0; j < kSub; ++j) tma_store_4d(&tmap_o, sO + j * kSubBytes, j * 64, tile_row0, head, batch);
+        if (p.seqlens != nullptr) tmap_acquire(mo);
+        for (int j = 0; j < kSub; ++j) tma_store_4d(mo, sO + j * kSubBytes, j * 64, tile_row0, head, bc);
         bulk_commit_group();
         bulk_wait_group_read<0>();
       }
@@ -703,7 +718,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       float* lse_row = p.lse + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride;
       if (half == 0 && row < p.lse_stride) {
         float lse = 0.f;
-        if (row < p.Sq) lse = (l > 0.f) ? m_ref + lg2_approx(l) : -INFINITY;
+        if (row < Sq) lse = (l > 0.f) ? m_ref + lg2_approx(l) : -INFINITY;
         lse_row[row] = lse;
       }
     }

@@ -233,6 +233,11 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 // ------------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------------
+// acquire a tensor map another kernel published to global memory with tensormap.cp_fenceproxy (varlen_sm100.cu)
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

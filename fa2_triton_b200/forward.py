@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -47,6 +48,18 @@ def padded_head_dim(head_dim: int) -> int:
 
 def pad_last(x: Tensor, d: int) -> Tensor:
     return x if x.shape[-1] == d else torch.nn.functional.pad(x, (0, d - x.shape[-1]))
+
+
+def device_sequence_lengths(attention_mask: Tensor) -> Tensor:
+    """int32 [B] lengths of a right-padded [B, S] mask, computed and kept on the device."""
+    return attention_mask.sum(dim=1, dtype=torch.int32).contiguous()
+
+
+def varlen_in_kernel(q: Tensor, k: Tensor, v: Tensor) -> bool:
+    """Variable-length batches run in one launch when the kernels can address the tensors as they are (head dim a
+    multiple of 8 up to 128, 16-bit dtype); anything else takes the per-sequence path below."""
+    return (runs_natively(q.shape[-1]) and q.dtype in (torch.float16, torch.bfloat16)
+            and os.environ.get("FA2_VARLEN_PER_SEQUENCE", "0") != "1")
 
 
 def sequence_lengths(attention_mask: Tensor):
@@ -123,6 +136,25 @@ def _flash_attn_forward(
         o = torch.zeros_like(q)
         seqlen_q_rounded = math.ceil(seqlen_q / 128) * 128
         lse = torch.zeros((batch, nheads_q, seqlen_q_rounded), device=q.device, dtype=torch.float32)
+        if varlen_in_kernel(q, k, v):
+            # One launch over the whole padded batch: the lengths stay on the device (no .item() / .tolist() sync) and a
+            # setup kernel derives per-sequence tensor maps from them (include/fa2_sm100.h, fa2_sm100_fwd_varlen).
+            assert nheads_q % nheads_kv == 0, f"{nheads_q = } is not divisible by {nheads_kv =}"
+            assert k.shape == expected_kv_shape and v.shape == expected_kv_shape
+            assert q.dtype == k.dtype == v.dtype, "All tensors must have the same type"
+            assert q.is_cuda and k.is_cuda and v.is_cuda and attention_mask.is_cuda
+            lib = _lib.load()
+            with torch.cuda.device(q.device):
+                seqlens = device_sequence_lengths(attention_mask)
+                tmap_ws = torch.empty(lib.fa2_sm100_varlen_workspace_bytes(batch), device=q.device, dtype=torch.uint8)
+                code = lib.fa2_sm100_fwd_varlen(
+                    q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                    batch, nheads_q, nheads_kv, seqlen_q, head_dim,
+                    _lib.strides3(q), _lib.strides3(k), _lib.strides3(v), _lib.strides3(o),
+                    seqlen_q_rounded, scale, int(bool(causal)), encode_dtype(q),
+                    seqlens.data_ptr(), tmap_ws.data_ptr(), tmap_ws.numel(), _stream_ptr(q.device))
+            _lib.check(code, "fa2_sm100_fwd_varlen")
+            return o, lse, scale, 0 if dropout_seed is None else dropout_seed
         for b, n in enumerate(sequence_lengths(attention_mask)):
             if n == 0:
                 continue

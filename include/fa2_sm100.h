@@ -10,6 +10,8 @@
  *   fa2_sm100_fwd_ext / fa2_sm100_bwd_ext: the same two launch sites with the reference's optional arguments
  *                               `bias` (src/forward/caller.py:66, 89, 97) and forward dropout (`dropout_p`,
  *                               `dropout_seed`, src/forward/caller.py:67, 91-92)
+ *   fa2_sm100_*_varlen       <- the same launch sites in the reference's VARLEN mode (cum_seqlens_q argument,
+ *                               src/forward/caller.py:46-59, src/backward/caller.py:56-79), without its pack / unpack copies
  *   fa2_sm100_dq_convert     <- the fp32 `dq` the reference allocates at src/backward/caller.py:86
  *                               (in the atomic modes our dQ accumulator is an opaque tile-swizzled workspace; this
  *                               call turns it into the caller-visible [B, Sq, Hq, D] tensor)
@@ -44,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 8
+#define FA2_SM100_ABI_VERSION 9
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -141,6 +143,41 @@ int fa2_sm100_bwd_ext(const void* dout, const void* q, const void* k, const void
                       const int64_t dv_strides[3],
                       int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype,
                       const void* bias, int bias_dtype, const int64_t bias_strides[3], void* stream);
+
+/* ---- variable-length batches (the reference's attention_mask mode, src/forward/caller.py:25-59) ----
+ * Tensors stay right-padded [B, S, H, D]; `seqlens` is a DEVICE array of B int32 lengths (query and key lengths coincide,
+ * src/forward/caller.py:28; values are clamped to [0, S]). Nothing is packed or unpacked and the host never reads a
+ * length: a small setup kernel derives, for every batch element, tensor maps bounded by its length (tensormap.replace),
+ * into `tmap_workspace` (device, fa2_sm100_varlen_workspace_bytes(B) bytes, 128-byte aligned, must stay untouched until
+ * the call's kernels have run), and every attention kernel runs ONCE over the whole batch. TMA zero-fills rows at or
+ * beyond a sequence's end on load and clips them on store, so the content of the padding (NaNs included) cannot reach a
+ * result. Rows of o / lse / dq / dk / dv that belong to the padding are NOT written: pass them zero-filled, as the
+ * reference allocates them (src/utils.py:26, src/forward/caller.py:70-74, src/backward/caller.py:86-88).
+ * fa2_sm100_bwd_varlen takes `deterministic` = 5 (FA2_DQ_DET_SPILL), 3 (FA2_DQ_NONE) or 6; the workspace size is that of
+ * the padded shape (fa2_sm100_bwd_workspace_bytes with Sq = Sk = S). */
+size_t fa2_sm100_varlen_workspace_bytes(int B);
+
+int fa2_sm100_fwd_varlen(const void* q, const void* k, const void* v, void* o, float* lse,
+                         int B, int Hq, int Hkv, int S, int D,
+                         const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                         const int64_t o_strides[3], int64_t lse_row_stride,
+                         float softmax_scale, int causal, int dtype,
+                         const int32_t* seqlens, void* tmap_workspace, size_t tmap_workspace_bytes, void* stream);
+
+int fa2_sm100_bwd_delta_varlen(const void* o, const void* dout, float* delta,
+                               int B, int Hq, int S, int D,
+                               const int64_t o_strides[3], const int64_t do_strides[3], int64_t lse_row_stride,
+                               int dtype, const int32_t* seqlens, void* stream);
+
+int fa2_sm100_bwd_varlen(const void* dout, const void* q, const void* k, const void* v,
+                         const float* lse, const float* delta,
+                         void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes,
+                         int B, int Hq, int Hkv, int S, int D,
+                         const int64_t do_strides[3], const int64_t q_strides[3], const int64_t k_strides[3],
+                         const int64_t v_strides[3], const int64_t dq_strides[3], const int64_t dk_strides[3],
+                         const int64_t dv_strides[3],
+                         int64_t lse_row_stride, float softmax_scale, int causal, int deterministic, int dtype, int dq_dtype,
+                         const int32_t* seqlens, void* tmap_workspace, size_t tmap_workspace_bytes, void* stream);
 
 /* dq[b, i, h, :] = softmax_scale * accumulator[b, h, i, :], written as `out_dtype` (16, 17 or 32). Called by
  * fa2_sm100_bwd itself in modes 0 and 2; exported for callers that keep several accumulators in flight. */

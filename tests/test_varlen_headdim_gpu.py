@@ -69,6 +69,45 @@ def test_attention_mask_ignores_padded_content():
         assert torch.equal(x, y)
 
 
+def test_attention_mask_padding_may_hold_nans_and_lengths_zero_and_one():
+    """The per-sequence tensor maps end at each sequence's length, so TMA never reads the padding: NaNs there cannot
+    reach a result (0 x NaN in a matrix product would). Lengths 0 and 1 are legal."""
+    B, S, H, D = 4, 300, 2, 128
+    q, k, v, do = generate_test_data(B, S, S, H, H, D, torch.bfloat16, DEV, seed=21)
+    mask = torch.zeros(B, S, dtype=torch.bool, device=DEV)
+    for b, n in enumerate((300, 129, 1, 0)):
+        mask[b, :n] = True
+    a = ours(q, k, v, do, True, mask)
+    check(a, q, k, v, do, True, mask)
+    q2, k2, v2, do2 = (t.clone() for t in (q, k, v, do))
+    for t in (q2, k2, v2, do2):
+        t[~mask] = float("nan")
+    b_ = ours(q2, k2, v2, do2, True, mask)
+    for x, y in zip(a, b_):
+        assert torch.isfinite(y).all() and torch.equal(x, y)
+
+
+@pytest.mark.parametrize("D", [40, 64, 96])
+def test_attention_mask_one_launch_equals_one_launch_per_sequence(D, monkeypatch):
+    """The in-kernel variable-length path against the per-sequence path (FA2_VARLEN_PER_SEQUENCE=1): same kernels, same
+    tiles, same order of operations - bit-identical results, fp32 dQ included."""
+    B, S, Hq, Hkv = 3, 520, 4, 2
+    q, k, v, do = generate_test_data(B, S, S, Hq, Hkv, D, torch.float16, DEV, seed=D)
+    mask = right_padded_mask(B, S, seed=D)
+
+    def run():
+        o, lse, scale, seed = fa2._flash_attn_forward(q, k, v, mask, None, 0.0, True, None, None)
+        dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, mask, o, lse, 0.0, True, scale, seed, deterministic=5)
+        torch.cuda.synchronize()
+        return o, lse, dq, dk, dv
+
+    one = run()
+    monkeypatch.setenv("FA2_VARLEN_PER_SEQUENCE", "1")
+    per_seq = run()
+    for name, x, y in zip(("O", "LSE", "dQ", "dK", "dV"), one, per_seq):
+        assert torch.equal(x, y), name
+
+
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("D", [8, 16, 24, 32, 40, 59, 72, 80, 96, 104, 111, 120])
 def test_other_head_dims_match_oracle(D, causal):
