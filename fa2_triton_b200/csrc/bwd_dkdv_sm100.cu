@@ -118,8 +118,10 @@ __device__ __forceinline__ void st_global_cs_v4(void* p, uint32_t a, uint32_t b,
 
 }  // namespace
 
-// kBias: the variant that adds the attention bias to the recomputed scores (extras.cuh)
-template <int D, bool kBf16, bool kSpill, bool kBias>
+// kExtra: 0 = the plain kernel; 1 = adds the attention bias to the recomputed scores (extras.cuh); 2 = variable-length
+// batches (per-sequence lengths and tensor maps, varlen_sm100.cu). Separate instantiations: the compute warps of the plain
+// kernel have no register to spare (measured: the runtime-selected form spilled and cost 12 %).
+template <int D, bool kBf16, bool kSpill, int kExtra>
 __global__ void __launch_bounds__(kThreads, 1)
 fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -149,14 +151,17 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int batch = blockIdx.z;
   const int kv0 = nblk * kBlk;
   // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
-  int Sq = p.Sq, Sk = p.Sk, bc = batch;
-  const CUtensorMap *mq = &tmap_q, *mk = &tmap_k, *mv = &tmap_v, *mdo = &tmap_do, *mdk = &tmap_dk, *mdv = &tmap_dv;
-  if (p.seqlens != nullptr) {
-    Sq = Sk = p.seqlens[batch];
-    const CUtensorMap* m = p.vmaps + static_cast<size_t>(batch) * kVarlenMapsPerBatch;
-    mq = m; mk = m + 1; mv = m + 2; mdo = m + 3; mdk = m + 4; mdv = m + 5; bc = 0;
-    if (kv0 >= Sk) return;  // key block in the padding: its dK / dV rows were zero-filled by the caller
-  }
+  constexpr bool kBias = kExtra == 1, kVarlen = kExtra == 2;
+  const int len = kVarlen ? p.seqlens[batch] : 0;
+  const int Sq = kVarlen ? len : p.Sq, Sk = kVarlen ? len : p.Sk, bc = kVarlen ? 0 : batch;
+  const CUtensorMap* vm = kVarlen ? p.vmaps + static_cast<size_t>(batch) * kVarlenMapsPerBatch : nullptr;
+  const CUtensorMap* mq = kVarlen ? vm : &tmap_q;
+  const CUtensorMap* mk = kVarlen ? vm + 1 : &tmap_k;
+  const CUtensorMap* mv = kVarlen ? vm + 2 : &tmap_v;
+  const CUtensorMap* mdo = kVarlen ? vm + 3 : &tmap_do;
+  const CUtensorMap* mdk = kVarlen ? vm + 4 : &tmap_dk;
+  const CUtensorMap* mdv = kVarlen ? vm + 5 : &tmap_dv;
+  if (kVarlen && kv0 >= Sk) return;  // key block in the padding: its dK / dV rows were zero-filled by the caller
   const int n_q_blocks = (Sq + kBlk - 1) / kBlk;
   const int group = p.Hq / p.Hkv;
   const int shift = Sk - Sq;
@@ -170,7 +175,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   if (warp == kTmaWarp && lane == 0) {
-    if (p.seqlens != nullptr) {  // maps published by fa2_varlen_maps_kernel
+    if constexpr (kVarlen) {  // maps published by fa2_varlen_maps_kernel
       tmap_acquire(mq);
       tmap_acquire(mk);
       tmap_acquire(mv);
@@ -180,7 +185,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tma_prefetch_desc(mk);
     tma_prefetch_desc(mv);
     tma_prefetch_desc(mdo);
-    if (p.seqlens == nullptr) {
+    if constexpr (!kVarlen) {
       tma_prefetch_desc(mdk);
       tma_prefetch_desc(mdv);
     }
@@ -544,7 +549,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     fence_proxy_async_smem();
     named_bar_sync(1, kCmpThreads);
     if (threadIdx.x == 0) {
-      if (p.seqlens != nullptr) {
+      if constexpr (kVarlen) {
         tmap_acquire(mdk);
         tmap_acquire(mdv);
       }
@@ -1060,11 +1065,11 @@ cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUten
   return cudaErrorInvalidValue;
 }
 
-template <int D, bool kBf16, bool kSpill, bool kBias>
+template <int D, bool kBf16, bool kSpill, int kExtra>
 static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                      const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
                                      const DkdvParams& p, cudaStream_t stream) {
-  auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kBias>;
+  auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kExtra>;
   constexpr int smem = DkdvSmem<D>::kBytes;
   static bool configured[64] = {};
   int dev = 0;
@@ -1082,11 +1087,14 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
 cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                             const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk,
                             const CUtensorMap& tdv, const DkdvParams& p, cudaStream_t stream) {
-  const bool has_bias = p.bias.ptr != nullptr;
+  const int extra = p.seqlens != nullptr ? 2 : (p.bias.ptr != nullptr ? 1 : 0);
+  if (p.seqlens != nullptr && p.bias.ptr != nullptr) return cudaErrorInvalidValue;
 #define FA2_DKDV_CASE(DD, BF, SP)                                                                                     \
-  if (D == DD && bf16 == BF && spill == SP)                                                                           \
-    return has_bias ? launch_bwd_dkdv_t<DD, BF, SP, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)                       \
-                    : launch_bwd_dkdv_t<DD, BF, SP, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
+  if (D == DD && bf16 == BF && spill == SP) {                                                                         \
+    if (extra == 0) return launch_bwd_dkdv_t<DD, BF, SP, 0>(tq, tk, tv, tdo, tdk, tdv, p, stream);                    \
+    if (extra == 1) return launch_bwd_dkdv_t<DD, BF, SP, 1>(tq, tk, tv, tdo, tdk, tdv, p, stream);                    \
+    return launch_bwd_dkdv_t<DD, BF, SP, 2>(tq, tk, tv, tdo, tdk, tdv, p, stream);                                    \
+  }
   FA2_DKDV_CASE(128, true, true) FA2_DKDV_CASE(128, true, false) FA2_DKDV_CASE(128, false, true) FA2_DKDV_CASE(128, false, false)
   FA2_DKDV_CASE(64, true, true) FA2_DKDV_CASE(64, true, false) FA2_DKDV_CASE(64, false, true) FA2_DKDV_CASE(64, false, false)
 #undef FA2_DKDV_CASE
