@@ -71,3 +71,23 @@ def triton_golden_extras(g):
         keep = np.unpackbits(g["dropout_keep"])[: B * H * Sq * Sk].astype(bool).reshape(B, H, Sq, Sk)
         p = float(g["dropout_p"])
     return seqlens, bias, keep, p
+
+
+def philox_keep_mask_torch(seed, p, B, H, Sq, Sk, device):
+    """oracle/philox.py on the GPU (int64 arithmetic): the reference's dropout keep-mask for large shapes."""
+    M32 = 0xFFFFFFFF
+    c0 = torch.arange(B * H * Sq * Sk, dtype=torch.int64, device=device) & M32
+    c1 = torch.zeros_like(c0)
+    c2 = torch.zeros_like(c0)
+    c3 = torch.zeros_like(c0)
+    k0, k1 = int(seed) & M32, (int(seed) >> 32) & M32
+    for _ in range(10):
+        pa, pb = 0xD2511F53 * c0, 0xCD9E8D57 * c2  # < 2^64 as unsigned; int64 wraps, the low 32 bits and the
+        hi_a = ((pa >> 32) & M32)                   # logical high word are recovered with masks
+        hi_b = ((pb >> 32) & M32)
+        c0, c1, c2, c3 = hi_b ^ c1 ^ k0, pb & M32, hi_a ^ c3 ^ k1, pa & M32
+        k0, k1 = (k0 + 0x9E3779B9) & M32, (k1 + 0xBB67AE85) & M32
+    x = torch.where(c0 >= 2**31, c0 - 2**32, c0)  # reinterpret as int32
+    x = torch.where(x < 0, -x - 1, x)
+    u = x.to(torch.float32) * torch.tensor(4.6566127342e-10, dtype=torch.float32, device=device)
+    return (u > torch.tensor(p, dtype=torch.float32, device=device)).reshape(B, H, Sq, Sk)
