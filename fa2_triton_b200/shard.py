@@ -84,16 +84,41 @@ def shard_views(q: Tensor, k: Tensor, v: Tensor, world_size: int, rank: int, *ex
     return out
 
 
+def shard_mask_and_bias(block, nheads_q: int, nheads_kv: int, attention_mask: Optional[Tensor],
+                        attention_bias: Optional[Tensor]):
+    """This block's part of the per-call extras: the ``[B, S]`` attention mask is cut along the batch, a
+    ``[1 | B, 1 | Hq, Sq, Sk]`` bias along whichever of its first two dimensions is not broadcast (views)."""
+    b0, b1, h0, h1 = block
+    group = nheads_q // nheads_kv
+    mask = None if attention_mask is None else attention_mask[b0:b1]
+    bias = attention_bias
+    if bias is not None:
+        if bias.size(0) > 1:
+            bias = bias[b0:b1]
+        if bias.size(1) > 1:
+            bias = bias[:, h0 * group:h1 * group]
+    return mask, bias
+
+
 def sharded_attention(q: Tensor, k: Tensor, v: Tensor, world_size: int, rank: int, causal: bool = False,
-                      softmax_scale: Optional[float] = None, attn: Optional[Callable] = None):
+                      softmax_scale: Optional[float] = None, attn: Optional[Callable] = None,
+                      attention_mask: Optional[Tensor] = None, attention_bias: Optional[Tensor] = None):
     """Run attention on this rank's (batch, head) slices of globally-shaped q, k, v (every rank holds, or can
     view, the tensors it owns; slices of other ranks are never touched). Returns ``[(block, out_view), ...]``.
-    ``attn`` defaults to :func:`fa2_triton_b200.flash_attn_func`; tests substitute a CPU function."""
+    ``attn`` defaults to :func:`fa2_triton_b200.flash_attn_func`; tests substitute a CPU function.
+    ``attention_mask`` / ``attention_bias`` are sliced with the tensors. Dropout is not offered here: the reference's
+    mask is numbered over the whole ``[B, Hq, Sq, Sk]`` score tensor (src/forward/kernel.py:147-149), a shard would
+    draw a different one."""
     if attn is None:
         from .wrapper import flash_attn_func as attn
     results = []
+    Hq, Hkv = q.shape[2], k.shape[2]
     for block, qs, ks, vs in shard_views(q, k, v, world_size, rank):
-        results.append((block, attn(qs, ks, vs, causal=causal, softmax_scale=softmax_scale)))
+        kw = {}
+        if attention_mask is not None or attention_bias is not None:
+            mask, bias = shard_mask_and_bias(block, Hq, Hkv, attention_mask, attention_bias)
+            kw = dict(attention_mask=mask, attention_bias=bias)
+        results.append((block, attn(qs, ks, vs, causal=causal, softmax_scale=softmax_scale, **kw)))
     return results
 
 
