@@ -87,6 +87,8 @@ CASES = {
     "triton_causal_fp16_b1h2s256d128": (1, 256, 256, 2, 2, 128, True, {}),
     "triton_ragged_gqa_fp16_b2h4kv2sq113sk203d40": (2, 113, 203, 4, 2, 40, False, {}),
     "triton_causal_sq_lt_sk_fp16_b1h2sq65sk200d128": (1, 65, 200, 2, 1, 128, True, {}),
+    # several 128-wide key blocks per query block with the B200-sized tiles: the online-softmax rescale path
+    "triton_causal_multiblock_gqa_fp16_b1h2kv1sq384sk640d128": (1, 384, 640, 2, 1, 128, True, {}),
     "triton_causal_sq_gt_sk_fp16_b1h2sq200sk72d64": (1, 200, 72, 2, 2, 64, True, {}),
     "triton_varlen_causal_fp16_b3h2s96d64": (3, 96, 96, 2, 2, 64, True, {"lengths": (96, 70, 1)}),
     "triton_bias_fp16_b2h2sq108sk256d64": (2, 108, 256, 2, 2, 64, False, {"bias": True}),
@@ -104,6 +106,9 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     dt = torch.float16
     for name, (B, Sq, Sk, Hq, Hkv, D, causal, extra) in CASES.items():
+        if (OUT / f"{name}.npz").exists() and "--all" not in sys.argv:
+            print(f"{name}: exists (pass --all to regenerate)")
+            continue
         # same recipe as the reference's tests/utils.py:21-25 (seed 0; Q,K,V ~ N(0, 0.5), dO ~ N(0, 1))
         torch.manual_seed(0)
         q = torch.empty(B, Sq, Hq, D, dtype=dt).normal_(0, 0.5)
