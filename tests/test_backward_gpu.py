@@ -68,10 +68,40 @@ def test_backward_fp32_dq_like_the_reference():
         assert_close_16("dV", dv, ref[3])
 
 
-@pytest.mark.parametrize("Hq,Hkv", [(8, 2), (4, 1)])
+@pytest.mark.parametrize("Hq,Hkv", [(8, 2), (4, 1), (8, 1), (24, 3)])
 @pytest.mark.parametrize("causal", [False, True])
 def test_backward_gqa(Hq, Hkv, causal):
     run_case(2, 300, 300, Hq, Hkv, 128, causal, torch.bfloat16)
+
+
+@pytest.mark.parametrize("Hq,Hkv", [(32, 1), (32, 2)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_backward_large_head_groups(Hq, Hkv, causal):
+    """16 and 32 query heads per kv head: dK / dV sum over the whole group (in fp32, inside one CTA) and reach 15-20,
+    where one bf16 unit in the last place is 0.06-0.125 - the fixed 2e-2 + 1e-2 |ref| bound is then tighter than the
+    output format (the same-precision eager arm misses it too, by more). The reference's own criterion applies: error
+    at most 3 x the same-precision eager error (tests/utils.py:126-133)."""
+    q, k, v, do = generate_test_data(2, 300, 300, Hq, Hkv, 128, torch.bfloat16, DEV, 0)
+    qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+    out = fa2.flash_attn_func(qq, kk, vv, causal=causal)
+    grads = torch.autograd.grad(out, (qq, kk, vv), do)
+    ref = er.fwd_bwd(q, k, v, do, causal=causal)
+    lowp = er.fwd_bwd(q, k, v, do, causal=causal, upcast=False, reorder_ops=True)
+    for name, got, r, lp in zip(("O", "dQ", "dK", "dV"), (out,) + tuple(grads), ref, lowp):
+        assert_reference_criterion(name, got, r, lp, 2 if name == "O" else 3, 5e-5 if name == "O" else 1e-5)
+        assert_close_16(name, got, r, atol=4e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("det", [False, 1, 5])
+def test_backward_mqa_every_dq_mode_and_only_some_gradients(det):
+    run_case(1, 384, 520, 16, 1, 64, True, torch.float16, deterministic=det)
+    q, k, v, do = generate_test_data(2, 256, 256, 16, 2, 128, torch.bfloat16, DEV, 4)
+    ref = er.fwd_bwd(q, k, v, do, causal=True)
+    kk, vv = k.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    dk, dv = torch.autograd.grad(fa2.flash_attn_func(q, kk, vv, causal=True), (kk, vv), do)
+    assert dk.shape == k.shape and dv.shape == v.shape
+    assert_close_16("dK", dk, ref[2])
+    assert_close_16("dV", dv, ref[3])
 
 
 def test_backward_fully_masked_rows_have_zero_dq():
