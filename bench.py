@@ -362,9 +362,15 @@ def main():
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        # two steps in flight (HostAttention.submit / HostTicket.result): every step still uploads its own inputs and
+        # downloads its own results inside the timed region; the next step's upload overlaps this step's download
+        prev = None
         for _ in range(n_e2e):
-            res = plan(*hp, causal=causal)
-            _ = float(res[0][0, 0, 0, 0])  # the host really holds the result
+            ticket = plan.submit(*hp, causal=causal)
+            if prev is not None:
+                _ = float(prev.result()[0][0, 0, 0, 0])  # the host really holds the result
+            prev = ticket
+        _ = float(prev.result()[0][0, 0, 0, 0])
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / n_e2e
         tt = torch.tensor([dt], device=dev, dtype=torch.float64)
@@ -373,7 +379,7 @@ def main():
         e2e = {"value": flops_global / tt.item() / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": plan.h2d_bytes,
                "d2h_bytes_per_step": plan.d2h_bytes, "ms_per_step": tt.item() * 1e3, "steps": n_e2e,
                "api": "fa2_triton_b200.host_api.HostAttention (pinned host q,k,v,dO in; o,dq,dk,dv out; "
-                      f"{plan.chunks} (batch, head range) chunks over 3 streams, pitched copies)"}
+                      f"{plan.chunks} (batch, head range) chunks over 3 streams, pitched copies, {plan.depth} steps in flight)"}
 
     # -------------------------------------------- CPU baseline (rank 0, N=1) --------------------------------------
     cpu = None
