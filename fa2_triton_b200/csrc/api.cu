@@ -221,6 +221,10 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
   p.scale_log2 = softmax_scale * kLog2e;
   p.causal = causal ? 1 : 0;
   p.n_pairs = (Sq + 255) / 256;
+  // A/B switch for measurements: FA2_SM100_NO_DTRIM=1 issues the products of the zero-filled columns as well
+  static const bool no_dtrim = [] { const char* e = getenv("FA2_SM100_NO_DTRIM"); return e && e[0] == '1'; }();
+  p.d_steps = no_dtrim ? kernel_head_dim(D) / 16 : (D + 15) / 16;
+  p.d_cols = no_dtrim ? kernel_head_dim(D) : round_up(D, 16);
   if (int e = make_bias_view(&p.bias, bias, bias_dtype, bias_strides, dtype)) return e;
   p.bias_mul = 1.0f / softmax_scale;
   p.dropout_p = dropout_p;
@@ -465,6 +469,9 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       k.bias = bias_view;
       k.seqlens = seqlens;
       k.vmaps = vmaps;
+      static const bool no_dtrim = [] { const char* e = getenv("FA2_SM100_NO_DTRIM"); return e && e[0] == '1'; }();
+      k.d_steps = no_dtrim ? Dk / 16 : (D + 15) / 16;
+      k.d_cols = no_dtrim ? Dk : round_up(D, 16);
       if (nonpersistent || bias || seqlens || D != Dk) ce = fa2::launch_bwd_dkdv(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
       else ce = fa2::launch_bwd_dkdv_persistent(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
     }

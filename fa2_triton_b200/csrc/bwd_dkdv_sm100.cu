@@ -253,7 +253,8 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // ========================================== MMA issuer =========================================
       if (T > 0 && elect_one()) {
         constexpr uint32_t idesc_kk = make_idesc_f16(kBlk, kBlk, kBf16, false, false);  // S^T, dP^T
-        constexpr uint32_t idesc_tn = make_idesc_f16(kBlk, D, kBf16, false, true);      // dV, dK
+        const uint32_t idesc_tn = make_idesc_f16(kBlk, p.d_cols, kBf16, false, true);  // dV, dK: N = the tensors' head dim (x16)
+        const int d_steps = p.d_steps;
         // K-major views (rows of the tile are the M/N index, the reduction runs along the 128-byte rows)
         const SmemDesc k_kmaj = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
         const SmemDesc v_kmaj = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
@@ -268,7 +269,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
-            umma_ss(d_tmem, advance(a, off), advance(b, off), idesc_kk, k > 0 ? 1u : 0u);
+            if (k < d_steps) umma_ss(d_tmem, advance(a, off), advance(b, off), idesc_kk, k > 0 ? 1u : 0u);
           }
         };
         // [128 kv x 128 q] (P^T or dS^T, 16-bit, in tensor memory) x [128 q x D] (dO or Q, MN-major), reduction over q.

@@ -148,7 +148,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
     // ========================================== MMA issuer =========================================
     if (elect_one()) {
       // dQ[q, d] (+)= sum_kv dS^T[kv, q] K[kv, d]: both operands MN-major (the rows of either tile are the reduction index)
-      constexpr uint32_t idesc = make_idesc_f16(kBlk, D, kBf16, true, true);
+      const uint32_t idesc = make_idesc_f16(kBlk, (p.d_actual + 15) / 16 * 16, kBf16, true, true);  // N = the tensors' head dim (x16)
       uint32_t c = 0;
       for (uint32_t t = 0;; ++t) {
         const uint32_t slot = t % kSchedSlots;

@@ -45,6 +45,9 @@ struct FwdParams {
   uint32_t seed_lo, seed_hi;
   const int* seqlens;         // variable-length mode (see above), else nullptr
   const CUtensorMap* vmaps;
+  // head dims below the kernel's: the zero columns TMA fills in need no products. d_steps = ceil(d / 16) k-steps of
+  // Q K^T, d_cols = d rounded up to 16 = the N of P V. Equal to D / 16 and D for a full head dim.
+  int d_steps, d_cols;
 };
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -154,6 +157,7 @@ struct DkdvParams {
   BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
   const int* seqlens;     // variable-length mode (one CTA per key block only), else nullptr
   const CUtensorMap* vmaps;
+  int d_steps, d_cols;    // as in FwdParams: k-steps of the products that reduce over the head dim, N of those that span it
 };
 cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                                        const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,

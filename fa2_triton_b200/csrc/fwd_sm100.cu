@@ -244,7 +244,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // ======================================== MMA issuer ========================================
     if (nblk_max > 0 && elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kBM, kBN, kBf16, false, false);
-      constexpr uint32_t idesc_pv = make_idesc_f16(kBM, D, kBf16, false, true);
+      const uint32_t idesc_pv = make_idesc_f16(kBM, p.d_cols, kBf16, false, true);  // N = the tensors' head dim (x16)
+      const int d_steps = p.d_steps;
       const int nblk[2] = {nblk0, nblk1};
 
       const SmemDesc q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);       // K-major
@@ -256,7 +257,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
-          umma_ss(tmem_base + t * kBN, advance(qa, off), advance(ka, off), idesc_qk, k > 0 ? 1u : 0u);
+          if (k < d_steps) umma_ss(tmem_base + t * kBN, advance(qa, off), advance(ka, off), idesc_qk, k > 0 ? 1u : 0u);
         }
       };
       auto issue_pv = [&](int t, int stage, bool accumulate) {
