@@ -55,6 +55,7 @@ SIGNATURES = {
     "fa2_sm100_bwd_delta": (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)] * 2
                             + [_c_int64, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "fa2_sm100_bwd_workspace_bytes": (_c_size_t, [_c_int] * 7),
+    "fa2_sm100_bwd_workspace_bytes_gqa": (_c_size_t, [_c_int] * 8),
     "fa2_sm100_bwd": (_c_int, [_c_void_p] * 10 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 7
                       + [_c_int64, _c_float, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "fa2_sm100_bwd_ext": (_c_int, [_c_void_p] * 10 + [_c_size_t] + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 7

@@ -194,8 +194,9 @@ def _flash_attn_backward(
         ptr = lambda t: t.data_ptr() if t is not None else None
         s3 = lambda t, like: _lib.strides3(t if t is not None else like)
         fused = mode in (_lib.DQ_ATOMIC, _lib.DQ_FUSED_ORDERED)
-        ws_args = (batch_size, nheads_q, seqlen_q, seqlen_k, head_dim, int(bool(causal)))
-        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(*ws_args, mode)
+        # the _gqa size leaves room for the fp32 partials of split head groups (MQA / large GQA groups)
+        ws_args = (batch_size, nheads_q, nheads_kv, seqlen_q, seqlen_k, head_dim, int(bool(causal)))
+        ws_bytes = lib.fa2_sm100_bwd_workspace_bytes_gqa(*ws_args, mode)
         workspace = None
         if auto and mode == _lib.DQ_DET_SPILL:
             if ws_bytes <= _spill_limit_bytes():
@@ -205,7 +206,7 @@ def _flash_attn_backward(
                     workspace = None
             if workspace is None:  # no room for the dS tiles: the recomputing dQ kernel needs 256 bytes
                 mode = _lib.DQ_DETERMINISTIC
-                ws_bytes = lib.fa2_sm100_bwd_workspace_bytes(*ws_args, mode)
+                ws_bytes = lib.fa2_sm100_bwd_workspace_bytes_gqa(*ws_args, mode)
         if workspace is None and ws_bytes:
             workspace = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
         ws_ptr = workspace.data_ptr() if ws_bytes else None

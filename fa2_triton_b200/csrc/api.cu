@@ -87,6 +87,26 @@ int check_common(int B, int Hq, int Hkv, int Sq, int Sk, int D, int dtype) {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// Into how many parts the dK / dV kernel cuts the group of query heads that share a kv head (see
+// fa2_sm100_bwd_workspace_bytes_gqa in the header). Looks at the group size only, so that a (batch, kv-head) shard of a
+// call makes the same choice as the whole call and stays bit-identical to it.
+int kv_split_of(int Hq, int Hkv, int D, int deterministic) {
+  static const bool off = [] { const char* e = getenv("FA2_SM100_NO_KV_SPLIT"); return e && e[0] == '1'; }();
+  if (off || Hkv < 1 || Hq % Hkv) return 1;
+  if (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED || deterministic == FA2_DQ_ONLY ||
+      deterministic == FA2_DQ_SPILL_DQ)
+    return 1;  // the fused kernel has no split variant; modes 4 and 7 do not run the dK / dV kernel
+  if (D != 64 && D != 128) return 1;
+  const int group = Hq / Hkv;
+  for (int s = 8; s >= 2; s /= 2)
+    if (group % s == 0 && group / s >= 4) return s;
+  return 1;
+}
+
+size_t kv_split_bytes(int B, int Hkv, int Sk, int D, int split) {  // the two fp32 partial tensors
+  return split > 1 ? 2 * static_cast<size_t>(B) * Sk * Hkv * split * D * sizeof(float) : 0;
+}
+
 // variable-length mode: per-sequence copies of the launch's tensor maps, built on the device (varlen_sm100.cu)
 struct VarlenTensor { const CUtensorMap* map; const void* ptr; int64_t batch_stride_elems; };
 
@@ -319,6 +339,12 @@ size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int c
   return accum + ((sem + 15) / 16) * 16;
 }
 
+size_t fa2_sm100_bwd_workspace_bytes_gqa(int B, int Hq, int Hkv, int Sq, int Sk, int D, int causal, int deterministic) {
+  const size_t base = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, Sk, D, causal, deterministic);
+  if (base == 0) return 0;
+  return (base + 15) / 16 * 16 + kv_split_bytes(B, Hkv, Sk, D, kv_split_of(Hq, Hkv, D, deterministic));
+}
+
 int fa2_sm100_bwd(const void* dout, const void* q, const void* k, const void* v, const float* lse, const float* delta,
                   void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int Hq, int Hkv,
                   int Sq, int Sk, int D, const int64_t do_strides[3], const int64_t q_strides[3],
@@ -443,6 +469,8 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
     ce = cudaMemsetAsync(workspace, 0, 128, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd scheduler counter memset");
   }
+  int kv_split_used = 1;
+  float* part_dk_used = nullptr;
   if (want_dkdv) {
     // A/B switches: FA2_SM100_OLD_DKDV=1 the unfused instantiation of the fused kernel (P^T in tensor memory, dS^T in
     // shared memory); FA2_SM100_DKDV_PERSISTENT=1 the persistent dK/dV kernel instead of one CTA per key block
@@ -469,6 +497,18 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       k.bias = bias_view;
       k.seqlens = seqlens;
       k.vmaps = vmaps;
+      // large query-head groups: split over several CTAs when the caller's workspace has room for the fp32 partials
+      // (sized with fa2_sm100_bwd_workspace_bytes_gqa); otherwise one CTA per (key block, kv head, batch) as before
+      int kv_split = (bias || seqlens || !nonpersistent) ? 1 : kv_split_of(Hq, Hkv, D, deterministic);
+      const size_t part_off = (need + 15) / 16 * 16;
+      if (kv_split > 1 && workspace_bytes < part_off + kv_split_bytes(B, Hkv, Sk, D, kv_split)) kv_split = 1;
+      k.kv_split = kv_split;
+      if (kv_split > 1) {
+        k.part_dk = reinterpret_cast<float*>(static_cast<char*>(workspace) + part_off);
+        k.part_dv = k.part_dk + static_cast<size_t>(B) * Sk * Hkv * kv_split * D;
+      }
+      kv_split_used = kv_split;
+      part_dk_used = k.part_dk;
       static const bool no_dtrim = [] { const char* e = getenv("FA2_SM100_NO_DTRIM"); return e && e[0] == '1'; }();
       k.d_steps = no_dtrim ? Dk / 16 : (D + 15) / 16;
       k.d_cols = no_dtrim ? Dk : round_up(D, 16);
@@ -476,6 +516,16 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       else ce = fa2::launch_bwd_dkdv_persistent(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
+    if (kv_split_used > 1) {
+      fa2::DkdvReduceParams r{};
+      r.part_dk = part_dk_used;
+      r.part_dv = part_dk_used + static_cast<size_t>(B) * Sk * Hkv * kv_split_used * D;
+      r.dk = dk; r.dv = dv;
+      for (int i = 0; i < 3; ++i) { r.dk_strides[i] = dk_strides[i]; r.dv_strides[i] = dv_strides[i]; }
+      r.B = B; r.Sk = Sk; r.Hkv = Hkv; r.D = D; r.kv_split = kv_split_used;
+      ce = fa2::launch_dkdv_reduce(dtype == FA2_DTYPE_BF16, r, st);
+      if (ce != cudaSuccess) return cuda_fail(ce, "fa2_dkdv_reduce_kernel launch");
+    }
   }
   if (!want_dq) return 0;
 

@@ -147,11 +147,12 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int lane = threadIdx.x & 31;
 
   const int nblk = static_cast<int>(blockIdx.x);  // causal: low key blocks are seen by the most query blocks - longest first
-  const int head_kv = blockIdx.y;
+  constexpr bool kBias = kExtra == 1, kVarlen = kExtra == 2, kSplit = kExtra == 3;
+  const int head_kv = blockIdx.y;  // kSplit: the (kv head, part) index; the query heads below follow from it unchanged
+  const int head_kv_src = kSplit ? head_kv / p.kv_split : head_kv;  // the kv head whose K / V rows are loaded
   const int batch = blockIdx.z;
   const int kv0 = nblk * kBlk;
   // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
-  constexpr bool kBias = kExtra == 1, kVarlen = kExtra == 2;
   const int len = kVarlen ? p.seqlens[batch] : 0;
   const int Sq = kVarlen ? len : p.Sq, Sk = kVarlen ? len : p.Sk, bc = kVarlen ? 0 : batch;
   const CUtensorMap* vm = kVarlen ? p.vmaps + static_cast<size_t>(batch) * kVarlenMapsPerBatch : nullptr;
@@ -163,7 +164,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const CUtensorMap* mdv = kVarlen ? vm + 5 : &tmap_dv;
   if (kVarlen && kv0 >= Sk) return;  // key block in the padding: its dK / dV rows were zero-filled by the caller
   const int n_q_blocks = (Sq + kBlk - 1) / kBlk;
-  const int group = p.Hq / p.Hkv;
+  const int group = kSplit ? p.Hq / (p.Hkv * p.kv_split) : p.Hq / p.Hkv;  // query heads this CTA loops over
   const int shift = Sk - Sq;
 
   // first query block that sees this key block (bottom-right aligned causal mask)
@@ -225,8 +226,8 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (T > 0 && elect_one()) {
         mbar_arrive_expect_tx(&bars[kKvFull], 2 * L::kTileBytes);
         for (int j = 0; j < kSub; ++j) {
-          tma_load_4d(sK + j * kSubBytes, mk, &bars[kKvFull], j * 64, kv0, head_kv, bc);
-          tma_load_4d(sV + j * kSubBytes, mv, &bars[kKvFull], j * 64, kv0, head_kv, bc);
+          tma_load_4d(sK + j * kSubBytes, mk, &bars[kKvFull], j * 64, kv0, head_kv_src, bc);
+          tma_load_4d(sV + j * kSubBytes, mv, &bars[kKvFull], j * 64, kv0, head_kv_src, bc);
         }
         for (int it = 0; it < T; ++it) {
           const int qs = it % kQStages, ds = it % kDoStages;
@@ -535,6 +536,19 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = 0u;
         }
+        if constexpr (kSplit) {
+          // fp32 partial of this part, straight from registers: 128 contiguous bytes per thread (key row) and chunk
+          if (kv < Sk) {
+            float* dst = (which == 0 ? p.part_dk : p.part_dv) +
+                         ((static_cast<int64_t>(batch) * Sk + kv) * (p.Hkv * p.kv_split) + head_kv) * D + col;
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4)
+              *reinterpret_cast<float4*>(dst + q4 * 4) =
+                  make_float4(__uint_as_float(o[q4 * 4 + 0]) * mul, __uint_as_float(o[q4 * 4 + 1]) * mul,
+                              __uint_as_float(o[q4 * 4 + 2]) * mul, __uint_as_float(o[q4 * 4 + 3]) * mul);
+          }
+          continue;
+        }
         uint8_t* sub = sOut + (col / 64) * kSubBytes;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -549,7 +563,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     fence_proxy_async_smem();
     named_bar_sync(1, kCmpThreads);
-    if (threadIdx.x == 0) {
+    if (!kSplit && threadIdx.x == 0) {
       if constexpr (kVarlen) {
         tmap_acquire(mdk);
         tmap_acquire(mdv);
@@ -1080,7 +1094,7 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv, p.B);
+  dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv * (kExtra == 3 ? p.kv_split : 1), p.B);
   kernel<<<grid, kThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
   return cudaGetLastError();
 }
@@ -1088,18 +1102,53 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
 cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                             const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk,
                             const CUtensorMap& tdv, const DkdvParams& p, cudaStream_t stream) {
-  const int extra = p.seqlens != nullptr ? 2 : (p.bias.ptr != nullptr ? 1 : 0);
+  const int extra = p.seqlens != nullptr ? 2 : (p.bias.ptr != nullptr ? 1 : (p.kv_split > 1 ? 3 : 0));
   if (p.seqlens != nullptr && p.bias.ptr != nullptr) return cudaErrorInvalidValue;
+  if (p.kv_split > 1 && extra != 3) return cudaErrorInvalidValue;
 #define FA2_DKDV_CASE(DD, BF, SP)                                                                                     \
   if (D == DD && bf16 == BF && spill == SP) {                                                                         \
     if (extra == 0) return launch_bwd_dkdv_t<DD, BF, SP, 0>(tq, tk, tv, tdo, tdk, tdv, p, stream);                    \
     if (extra == 1) return launch_bwd_dkdv_t<DD, BF, SP, 1>(tq, tk, tv, tdo, tdk, tdv, p, stream);                    \
-    return launch_bwd_dkdv_t<DD, BF, SP, 2>(tq, tk, tv, tdo, tdk, tdv, p, stream);                                    \
+    if (extra == 2) return launch_bwd_dkdv_t<DD, BF, SP, 2>(tq, tk, tv, tdo, tdk, tdv, p, stream);                    \
+    return launch_bwd_dkdv_t<DD, BF, SP, 3>(tq, tk, tv, tdo, tdk, tdv, p, stream);                                    \
   }
   FA2_DKDV_CASE(128, true, true) FA2_DKDV_CASE(128, true, false) FA2_DKDV_CASE(128, false, true) FA2_DKDV_CASE(128, false, false)
   FA2_DKDV_CASE(64, true, true) FA2_DKDV_CASE(64, true, false) FA2_DKDV_CASE(64, false, true) FA2_DKDV_CASE(64, false, false)
 #undef FA2_DKDV_CASE
   return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum of the fp32 dK / dV partials of the split head groups (kExtra == 3): fixed order, one rounding
+// ------------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(256) fa2_dkdv_reduce_kernel(const DkdvReduceParams p) {
+  const int64_t n4 = static_cast<int64_t>(p.B) * p.Sk * p.Hkv * (p.D / 4);  // float4 groups per output tensor
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < 2 * n4; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const bool is_dv = i >= n4;
+    const int64_t e = is_dv ? i - n4 : i;
+    const int d4 = static_cast<int>(e % (p.D / 4));
+    const int h = static_cast<int>((e / (p.D / 4)) % p.Hkv);
+    const int64_t bs = e / (p.D / 4) / p.Hkv;  // b * Sk + s
+    const float* src = (is_dv ? p.part_dv : p.part_dk) + ((bs * p.Hkv + h) * p.kv_split) * p.D + d4 * 4;
+    float4 acc = *reinterpret_cast<const float4*>(src);
+    for (int j = 1; j < p.kv_split; ++j) {
+      const float4 x = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(j) * p.D);
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    const int64_t* st = is_dv ? p.dv_strides : p.dk_strides;
+    const int b = static_cast<int>(bs / p.Sk), srow = static_cast<int>(bs % p.Sk);
+    uint16_t* dst = static_cast<uint16_t*>(is_dv ? p.dv : p.dk) + b * st[0] + h * st[1] + srow * st[2] + d4 * 4;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack2<kBf16>(acc.x, acc.y), pack2<kBf16>(acc.z, acc.w));
+  }
+}
+
+cudaError_t launch_dkdv_reduce(bool bf16, const DkdvReduceParams& p, cudaStream_t stream) {
+  const int64_t n = 2ll * p.B * p.Sk * p.Hkv * (p.D / 4);
+  const int blocks = static_cast<int>(n / 256 + 1 < 148 * 8 ? n / 256 + 1 : 148 * 8);
+  if (bf16) fa2_dkdv_reduce_kernel<true><<<blocks, 256, 0, stream>>>(p);
+  else fa2_dkdv_reduce_kernel<false><<<blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
 }
 
 }  // namespace fa2

@@ -158,7 +158,24 @@ struct DkdvParams {
   const int* seqlens;     // variable-length mode (one CTA per key block only), else nullptr
   const CUtensorMap* vmaps;
   int d_steps, d_cols;    // as in FwdParams: k-steps of the products that reduce over the head dim, N of those that span it
+  // kernel variant kExtra == 3 (large query-head groups): the grid's "kv head" index counts Hkv * kv_split parts, part
+  // i of kv head h covering the query heads [h * group + i * group / kv_split, ...); every part writes fp32 partial
+  // dK / dV to `part_dk` / `part_dv` ([B, Sk, Hkv * kv_split, D] fp32, contiguous) and fa2_dkdv_reduce_kernel sums them.
+  int kv_split;
+  float* part_dk;
+  float* part_dv;
 };
+
+// dk[b, s, h, :] = sum over the kv_split partials of kv head h, in a fixed order, rounded once to the output dtype
+struct DkdvReduceParams {
+  const float* part_dk;
+  const float* part_dv;
+  void* dk;
+  void* dv;
+  int64_t dk_strides[3], dv_strides[3];  // batch, head, seq (elements)
+  int B, Sk, Hkv, D, kv_split;
+};
+cudaError_t launch_dkdv_reduce(bool bf16, const DkdvReduceParams& p, cudaStream_t stream);
 cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                                        const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,
                                        cudaStream_t stream);

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 9
+#define FA2_SM100_ABI_VERSION 10
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -115,6 +115,16 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
  * (`causal` decides which pairs are visible; B=4, H=32, S=4096 causal: 2.06 GiB).
  * The workspace must be 16-byte aligned. */
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int causal, int deterministic);
+
+/* The same with room for splitting large groups of query heads: the dK / dV kernel runs one CTA per (key block, kv head,
+ * batch element) that loops over all Hq / Hkv query heads of the kv head - with few kv heads (MQA: B = 4, S = 4096 gives
+ * 128 CTAs of 32 heads each for 148 SMs) the grid neither fills nor balances the chip. Given a workspace of THIS size,
+ * fa2_sm100_bwd cuts a group of 8 or more query heads into 2, 4 or 8 parts of at least 4 heads, lets each part write fp32
+ * partial dK / dV to the tail of the workspace and sums them in a fixed order with one rounding (deterministic; the
+ * reference sums ALL query heads in 16-bit torch ops, src/backward/caller.py:163-165). With the smaller size above the
+ * call runs unsplit. The choice depends on the group size only: a (batch, kv-head) shard of a call stays bit-identical
+ * to the whole call. */
+size_t fa2_sm100_bwd_workspace_bytes_gqa(int B, int Hq, int Hkv, int Sq, int Sk, int D, int causal, int deterministic);
 
 /* dQ ([B, Sq, Hq, D], `dq_dtype` = the input dtype or 32 for fp32 as the reference allocates it at
  * src/backward/caller.py:86), dK and dV (input dtype, [B, Sk, Hkv, D], GQA head groups already summed).

@@ -228,3 +228,27 @@ def test_backward_skips_unneeded_gradients():
     out = fa2.flash_attn_func(q, kk, vv, causal=True)
     dk_only, dv_only = torch.autograd.grad(out, (kk, vv), do)
     assert torch.equal(dk_only, dk_all) and torch.equal(dv_only, dv_all)
+
+
+def test_kv_head_shards_equal_the_whole_call_bit_for_bit():
+    """The batch x head partitioner cuts a call into (batch, kv-head) slices; the head-group split of the dK / dV kernel
+    looks at the group size only, so every slice makes the whole call's choice: identical bits, GQA 16:2 (group 8, two
+    parts per kv head) over 4 "ranks"."""
+    from fa2_triton_b200 import shard
+    B, S, Hq, Hkv, D = 2, 384, 16, 2, 128
+    q, k, v, do = generate_test_data(B, S, S, Hq, Hkv, D, torch.bfloat16, DEV, 12)
+
+    def fwd_bwd(qs, ks, vs, dos):
+        qq, kk, vv = (t.detach().requires_grad_(True) for t in (qs, ks, vs))
+        out = fa2.flash_attn_func(qq, kk, vv, causal=True)
+        return (out.detach(),) + torch.autograd.grad(out, (qq, kk, vv), dos)
+
+    whole = fwd_bwd(q, k, v, do)
+    grp = Hq // Hkv
+    for rank in range(4):
+        for (b0, b1, h0, h1), qs, ks, vs, dos in shard.shard_views(q, k, v, 4, rank, do):
+            part = fwd_bwd(qs, ks, vs, dos)
+            assert torch.equal(part[0], whole[0][b0:b1, :, h0 * grp:h1 * grp])
+            assert torch.equal(part[1], whole[1][b0:b1, :, h0 * grp:h1 * grp])
+            assert torch.equal(part[2], whole[2][b0:b1, :, h0:h1])
+            assert torch.equal(part[3], whole[3][b0:b1, :, h0:h1])
