@@ -110,7 +110,7 @@ struct FwdSmem {
   static constexpr int kStageOff = (kXchgOff + 4 * 2 * 2 * kBM * 4 + 15) / 16 * 16;
   static constexpr int kStageRow = 80;
   static constexpr int kStageWarpBytes = 32 * kStageRow;
-  static constexpr int kBytes = kStageOff + (kExt ? (kSmxThreads / 32) * kStageWarpBytes : 0);
+  static constexpr int kBytes = kStageOff + ((kExt && kHalves == 1) ? (kSmxThreads / 32) * kStageWarpBytes : 0);
   static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-byte alignment
   static_assert(kDynBytes <= 227 * 1024, "forward shared memory exceeds the 227 KB a CTA can have");
 };

@@ -6,7 +6,7 @@ mkdir -p ../../variants
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   d=../../variants/obj_$name; mkdir -p $d
-  for f in api fwd_sm100 bwd_sm100 bwd_dkdv_sm100 bwd_dq_sm100 bwd_dq_spill_sm100 probe_sm100; do
+  for f in api fwd_sm100 bwd_sm100 bwd_dkdv_sm100 bwd_dq_sm100 bwd_dq_spill_sm100 varlen_sm100 probe_sm100; do
     nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $flags -c $f.cu -o $d/$f.o &
   done
   wait
