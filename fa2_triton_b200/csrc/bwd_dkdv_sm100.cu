@@ -153,7 +153,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int batch = blockIdx.z;
   const int kv0 = nblk * kBlk;
   // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
-  const int len = kVarlen ? p.seqlens[batch] : 0;
+  const int len = kVarlen ? min(max(p.seqlens[batch], 0), p.Sq) : 0;  // clamped like the tensor maps
   const int Sq = kVarlen ? len : p.Sq, Sk = kVarlen ? len : p.Sk, bc = kVarlen ? 0 : batch;
   const CUtensorMap* vm = kVarlen ? p.vmaps + static_cast<size_t>(batch) * kVarlenMapsPerBatch : nullptr;
   const CUtensorMap* mq = kVarlen ? vm : &tmap_q;

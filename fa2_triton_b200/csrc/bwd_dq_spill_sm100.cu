@@ -124,7 +124,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
         if (w >= n_items) break;
         const Item it = item_of(w, n_q_blocks, p.Hq);
         const int head_kv = it.head / group;
-        const int len = p.seqlens != nullptr ? p.seqlens[it.batch] : 0;  // variable-length mode: this sequence's length
+        const int len = p.seqlens != nullptr ? min(max(p.seqlens[it.batch], 0), p.Sq) : 0;  // variable-length mode: this sequence's length
         const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
                                               : visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
         const long long tile0 = (static_cast<long long>(it.batch) * p.Hq + it.head) * p.tiles_per_head +
@@ -157,7 +157,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
         mbar_arrive(&item_empty[slot]);
         if (w < 0) break;
         const Item it = item_of(w, n_q_blocks, p.Hq);
-        const int len = p.seqlens != nullptr ? p.seqlens[it.batch] : 0;  // variable-length mode: this sequence's length
+        const int len = p.seqlens != nullptr ? min(max(p.seqlens[it.batch], 0), p.Sq) : 0;  // variable-length mode: this sequence's length
         const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
                                               : visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
         const uint32_t buf = t & 1;
@@ -194,7 +194,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
       if (w < 0) break;
       const Item it = item_of(w, n_q_blocks, p.Hq);
       const int row = it.m * kBlk + r;
-      const int len = p.seqlens != nullptr ? p.seqlens[it.batch] : 0;  // variable-length mode: this sequence's length
+      const int len = p.seqlens != nullptr ? min(max(p.seqlens[it.batch], 0), p.Sq) : 0;  // variable-length mode: this sequence's length
         const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
                                               : visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
       const uint32_t buf = t & 1;

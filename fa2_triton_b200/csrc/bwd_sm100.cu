@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
   constexpr int kPasses = 4;  // rows per thread: all 2 x kPasses 16-byte loads are issued before the first use
   constexpr int kRowsPerBlock = kRowsPerPass * kPasses;
   const int head = blockIdx.y, batch = blockIdx.z;
-  const int sq_valid = p.seqlens != nullptr ? p.seqlens[batch] : p.Sq;  // variable-length mode: this sequence's rows
+  const int sq_valid = p.seqlens != nullptr ? min(max(p.seqlens[batch], 0), p.Sq) : p.Sq;  // variable-length mode: this sequence's rows
   const int row0 = blockIdx.x * kRowsPerBlock + threadIdx.x / kThreadsPerRow;
   const int part = threadIdx.x % kThreadsPerRow;
   const uint16_t* obase = reinterpret_cast<const uint16_t*>(p.o) + batch * p.o_strides[0] + head * p.o_strides[1] + part * 8;

@@ -166,7 +166,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   int Sq = p.Sq, Sk = p.Sk, bc = batch;
   const CUtensorMap *mq = &tmap_q, *mk = &tmap_k, *mv = &tmap_v, *mo = &tmap_o;
   if (p.seqlens != nullptr) {
-    Sq = Sk = p.seqlens[batch];
+    Sq = Sk = min(max(p.seqlens[batch], 0), p.Sq);  // clamped like the tensor maps (varlen_sm100.cu)
     const CUtensorMap* m = p.vmaps + static_cast<size_t>(batch) * kVarlenMapsPerBatch;
     mq = m; mk = m + 1; mv = m + 2; mo = m + 3; bc = 0;
     if (row0 >= Sq) return;  // tile pair in the padding: its rows of O and LSE were zero-filled by the caller

@@ -159,3 +159,31 @@ def test_head_dim_above_128_is_rejected():
     q, k, v, _ = generate_test_data(1, 128, 128, 2, 2, 256, torch.bfloat16, DEV)
     with pytest.raises(NotImplementedError):
         fa2.flash_attn_func(q, k, v)
+
+
+def test_varlen_abi_clamps_out_of_range_lengths():
+    """fa2_sm100_fwd_varlen with lengths outside [0, S] (only reachable through the C ABI): treated as S and 0."""
+    import math
+    from fa2_triton_b200 import _lib
+    lib = _lib.load()
+    B, S, H, D = 3, 200, 2, 64
+    q, k, v, _ = generate_test_data(B, S, S, H, H, D, torch.bfloat16, DEV, seed=31)
+
+    def run(lengths):
+        o = torch.zeros_like(q)
+        S_pad = math.ceil(S / 128) * 128
+        lse = torch.zeros(B, H, S_pad, device=DEV, dtype=torch.float32)
+        sl = torch.tensor(lengths, device=DEV, dtype=torch.int32)
+        ws = torch.empty(lib.fa2_sm100_varlen_workspace_bytes(B), device=DEV, dtype=torch.uint8)
+        rc = lib.fa2_sm100_fwd_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, H, H, S, D,
+                                      _lib.strides3(q), _lib.strides3(k), _lib.strides3(v), _lib.strides3(o), S_pad,
+                                      1.0 / math.sqrt(D), 1, 17, sl.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "fa2_sm100_fwd_varlen")
+        torch.cuda.synchronize()
+        return o, lse
+
+    a = run([S + 57, -4, 77])
+    b = run([S, 0, 77])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert (a[0][1] == 0).all()
