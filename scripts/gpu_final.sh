@@ -11,7 +11,7 @@ import json
 for n in ("final_bench", "final_bench_reference", "final_bench_cfg2", "final_bench_cfg4", "final_bench_cfg5"):
     try:
         d = json.load(open(f"gpurun_out/{n}.json"))
-        print(n, round(d["value"], 2), d["unit"], round(d["ms_per_step"], 3), "ms", d.get("e2e", {}).get("value"), d.get("clocks"))
+        print(n, round(d["value"], 2), d["unit"], round(d["ms_per_step"], 3), "ms", (d.get("e2e") or {}).get("value"), d.get("clocks"))
     except Exception as e:
         print(n, "ERR", e)
 PY
