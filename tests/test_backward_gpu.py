@@ -252,3 +252,31 @@ def test_kv_head_shards_equal_the_whole_call_bit_for_bit():
             assert torch.equal(part[1], whole[1][b0:b1, :, h0 * grp:h1 * grp])
             assert torch.equal(part[2], whole[2][b0:b1, :, h0:h1])
             assert torch.equal(part[3], whole[3][b0:b1, :, h0:h1])
+
+
+@pytest.mark.parametrize("kind", ["mqa_split", "varlen", "bias"])
+def test_new_paths_are_bit_repeatable(kind):
+    """tests/test_repeatability.py's intent (10 repeats, bit-identical outputs and gradients) for the paths added on top
+    of the plain one: split head groups (fp32 partials summed in a fixed order), the in-kernel variable-length path and
+    the bias variants."""
+    B, S, D = 3, 640, 128
+    Hq, Hkv = (16, 1) if kind == "mqa_split" else (4, 2)
+    q, k, v, do = generate_test_data(B, S, S, Hq, Hkv, D, torch.bfloat16, DEV, 17)
+    kw = {}
+    if kind == "varlen":
+        mask = torch.zeros(B, S, dtype=torch.bool, device=DEV)
+        for b, n in enumerate((640, 301, 77)):
+            mask[b, :n] = True
+        kw["attention_mask"] = mask
+    if kind == "bias":
+        kw["attention_bias"] = torch.rand(1, Hq, S, S, device=DEV).to(torch.bfloat16)
+
+    def once():
+        qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
+        out = fa2.flash_attn_func(qq, kk, vv, causal=True, **kw)
+        return (out.detach(),) + torch.autograd.grad(out, (qq, kk, vv), do)
+
+    first = once()
+    for _ in range(9):
+        for a, b in zip(first, once()):
+            assert torch.equal(a, b)
