@@ -173,7 +173,10 @@ def _flash_attn_backward(
         det = True  # the fused (atomic / ticket-ordered) kernel has no bias variant: the deterministic kernels serve it
     auto = isinstance(det, bool) and det  # True: spill when the workspace fits, else recompute
     if isinstance(det, bool):
-        mode = (_lib.DQ_DET_SPILL if q.shape[-1] > 64 else _lib.DQ_DETERMINISTIC) if det else _lib.DQ_ATOMIC
+        # with a bias the spilled-dS pair is preferred at every head dim: the recomputing dQ kernel has to fetch the bias a
+        # second time, row by row (measured at D = 64, config-3 shape: 5.6 ms against 1.6)
+        spill = q.shape[-1] > 64 or bias is not None
+        mode = (_lib.DQ_DET_SPILL if spill else _lib.DQ_DETERMINISTIC) if det else _lib.DQ_ATOMIC
     else:
         mode = int(det) if det in (0, 1, 2, 5) else int(bool(det))  # one of _lib.DQ_*
     if not need_dq and not need_dkdv:

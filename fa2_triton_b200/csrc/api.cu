@@ -495,6 +495,22 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       k.max_ctas = dkdv_ctas;  // experiments only (scripts/concurrent_probe.py): cap on the persistent grid
       for (int i = 0; i < 3; ++i) { k.dk_strides[i] = dk_strides[i]; k.dv_strides[i] = dv_strides[i]; }
       k.bias = bias_view;
+      CUtensorMap tbias;
+      if (bias && bias_dtype == dtype) {
+        // [1 | B, 1 | Hq, Sq, Sk] seen as a [B', Sq, H', Sk] tensor: same map builder as q / k / v. Only if TMA can address
+        // it (16-byte aligned base, strides multiples of 8 elements); the kernel's plain loads serve every other bias.
+        const int Bb = bias_strides[0] ? B : 1, Hb = bias_strides[1] ? Hq : 1;
+        const int64_t bs[3] = {bias_strides[0], bias_strides[1], bias_strides[2]};
+        const bool ok = reinterpret_cast<uintptr_t>(bias) % 16 == 0 && bs[0] % 8 == 0 && bs[1] % 8 == 0 && bs[2] % 8 == 0 &&
+                        bs[2] > 0;
+        static const bool no_bias_tma = [] { const char* e = getenv("FA2_SM100_NO_BIAS_TMA"); return e && e[0] == '1'; }();
+        if (ok && !no_bias_tma && make_tmap_bshd(&tbias, bias, dtype, Bb, Sq, Hb, Sk, bs, 128, "bias") == 0) {
+          k.bias_tma = 1;
+          k.bias_map = &tbias;
+          k.bias_head_mul = Hb > 1 ? 1 : 0;
+          k.bias_batch_mul = Bb > 1 ? 1 : 0;
+        }
+      }
       k.seqlens = seqlens;
       k.vmaps = vmaps;
       // large query-head groups: split over several CTAs when the caller's workspace has room for the fp32 partials

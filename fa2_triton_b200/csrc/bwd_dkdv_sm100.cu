@@ -77,21 +77,25 @@ __host__ __device__ constexpr bool emulate_pair(int q) {
        : FA2_DKDV_EMUL == 1 ? (q % 4 == 3) : false;
 }
 
-template <int D>
+// kQS: stages of the Q ring; kBiasTile: room for one [128 queries x 128 keys] 16-bit tile of the attention bias (the
+// bias variant; at head dim 128 it takes the place of the third Q stage)
+template <int D, int kQS = kQStages, bool kBiasTile = false>
 struct DkdvSmem {
   static constexpr int kTileBytes = kBlk * D * 2;  // K, V, Q, dO tiles
+  static constexpr int kBiasBytes = kBlk * kBlk * 2;
   static constexpr int kKOff = 0;
   static constexpr int kVOff = kKOff + kTileBytes;
   static constexpr int kQOff = kVOff + kTileBytes;
-  static constexpr int kDOOff = kQOff + kQStages * kTileBytes;
+  static constexpr int kBiasOff = kQOff + kQS * kTileBytes;  // multiples of 16 KB: 1024-byte aligned for the 128-byte swizzle
+  static constexpr int kDOOff = kBiasOff + (kBiasTile ? kBiasBytes : 0);
   // The LSE row of query block i rides with Q(i) (stage released by dK(i), i.e. after dS(i)). Its delta row rides with
   // dO(i), but is read by dS(i) - possibly after dV(i), which releases the dO stage, has retired: the slot has its own
   // "empty" barrier on which every compute thread arrives once it has its delta values. (Without it the load of block
   // i + 2 could overwrite the row under a late reader: run-to-run differences at S = 16384.)
-  static constexpr int kLseOff = kDOOff + kDoStages * kTileBytes;   // kQStages x 512 B
-  static constexpr int kDeltaOff = kLseOff + kQStages * kBlk * 4;   // kDoStages x 512 B
+  static constexpr int kLseOff = kDOOff + kDoStages * kTileBytes;   // kQS x 512 B
+  static constexpr int kDeltaOff = kLseOff + kQS * kBlk * 4;        // kDoStages x 512 B
   static constexpr int kBarOff = kDeltaOff + kDoStages * kBlk * 4;
-  static constexpr int kNumBars = 18;
+  static constexpr int kNumBars = 20;
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
   static constexpr int kBytes = kTmemSlotOff + 16;
   static_assert(kBytes <= 232448, "dK/dV kernel smem budget exceeded");
@@ -109,6 +113,8 @@ enum DkdvBar {
   kDsFull = 14,   // dS^T(i) is in tensor memory (over dP^T)
   kDkvFull = 15,
   kDeltaEmpty = 16,  // [2] every compute thread has read the delta row in this slot
+  kBiasFull = 18,    // bias variant: the bias tile of this iteration has landed
+  kBiasEmpty = 19,   // ... and every compute thread has read its values
 };
 
 // streaming 16-byte store (written once, read once by the dQ kernel: evict first)
@@ -126,8 +132,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                     const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
-                    const DkdvParams p) {
-  using L = DkdvSmem<D>;
+                    const __grid_constant__ CUtensorMap tmap_bias, const DkdvParams p) {
+  // the bias variant at head dim 128 gives its third Q stage to the bias tile
+  constexpr int kQS = (kExtra == 1 && D == 128) ? 2 : kQStages;
+  using L = DkdvSmem<D, kQS, kExtra == 1>;
   constexpr int kSub = D / 64;
   constexpr int kSubBytes = kBlk * 128;  // [128 rows x 64 x 16-bit]
   constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
@@ -138,6 +146,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* sV = smem + L::kVOff;
   uint8_t* sQ = smem + L::kQOff;
   uint8_t* sDO = smem + L::kDOOff;
+  [[maybe_unused]] uint8_t* sBias = smem + L::kBiasOff;
   float* sLse = reinterpret_cast<float*>(smem + L::kLseOff);
   float* sDelta = reinterpret_cast<float*>(smem + L::kDeltaOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -194,7 +203,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == kMmaWarp) {
     if (lane == 0) {
       mbar_init(&bars[kKvFull], 1);
-      for (int s = 0; s < kQStages; ++s) {
+      for (int s = 0; s < kQS; ++s) {
         mbar_init(&bars[kQFull + s], 1);
         mbar_init(&bars[kQEmpty + s], 1);
       }
@@ -203,6 +212,8 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mbar_init(&bars[kDoEmpty + s], 1);
         mbar_init(&bars[kDeltaEmpty + s], kCmpThreads);
       }
+      mbar_init(&bars[kBiasFull], 1);
+      mbar_init(&bars[kBiasEmpty], kCmpThreads);
       mbar_init(&bars[kSFull], 1);
       mbar_init(&bars[kPFull], kCmpThreads);
       mbar_init(&bars[kDpFull], 1);
@@ -230,11 +241,20 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tma_load_4d(sV + j * kSubBytes, mv, &bars[kKvFull], j * 64, kv0, head_kv_src, bc);
         }
         for (int it = 0; it < T; ++it) {
-          const int qs = it % kQStages, ds = it % kDoStages;
-          const uint32_t qph = (it / kQStages) & 1, dph = (it / kDoStages) & 1;
+          const int qs = it % kQS, ds = it % kDoStages;
+          const uint32_t qph = (it / kQS) & 1, dph = (it / kDoStages) & 1;
           const int head = head_kv * group + it / m_count;
           const int m = m_start + it % m_count;
           const int64_t row_off = (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
+          if constexpr (kBias) {
+            if (p.bias_tma) {  // bias tile (it): two [128 queries x 64 keys] sub-tiles; released by the readers of tile it - 1
+              mbar_wait(&bars[kBiasEmpty], (it & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars[kBiasFull], L::kBiasBytes);
+              for (int j = 0; j < 2; ++j)
+                tma_load_4d(sBias + j * (kBlk * 128), &tmap_bias, &bars[kBiasFull], kv0 + j * 64, m * kBlk,
+                            p.bias_head_mul * head, p.bias_batch_mul * batch);
+            }
+          }
           // Q(it) + its LSE row: released by dK(it - 3)
           mbar_wait(&bars[kQEmpty + qs], qph ^ 1);
           mbar_arrive_expect_tx(&bars[kQFull + qs], L::kTileBytes + kBlk * 4);
@@ -297,9 +317,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
         for (int it = 0; it < T; ++it) {
           const uint32_t par = it & 1;
-          const int qs = it % kQStages, qsn = (it + 1) % kQStages;
+          const int qs = it % kQS, qsn = (it + 1) % kQS;
           const int ds = it % kDoStages, dsn = (it + 1) % kDoStages;
-          const uint32_t qphn = ((it + 1) / kQStages) & 1, dphn = ((it + 1) / kDoStages) & 1;
+          const uint32_t qphn = ((it + 1) / kQS) & 1, dphn = ((it + 1) / kDoStages) & 1;
           // dV += P^T(it) dO(it)
           mbar_wait(&bars[kPFull], par);
           tcgen05_fence_after();
@@ -363,8 +383,8 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
     for (int it = 0; it < T; ++it) {
       const uint32_t par = it & 1;
-      const int qs = it % kQStages, ds = it % kDoStages;
-      const uint32_t qph = (it / kQStages) & 1, dph = (it / kDoStages) & 1;
+      const int qs = it % kQS, ds = it % kDoStages;
+      const uint32_t qph = (it / kQS) & 1, dph = (it / kDoStages) & 1;
       const int j_in_head = it % m_count;
       const int m = m_start + j_in_head;
       const int q0 = m * kBlk + wg * kCmpCols;  // first query column of this thread's slice
@@ -376,6 +396,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // 16-bit values travel as packed pairs, fp32 ones unpacked.
       uint32_t braw[kCmpCols];
       if constexpr (kBias) {
+        if (!p.bias_tma) {
         const int64_t off0 = batch * p.bias.sb + (head_kv * group + it / m_count) * p.bias.sh +
                              static_cast<int64_t>(q0) * p.bias.sm + kv;
         const bool col_ok = kv < Sk;
@@ -393,6 +414,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             braw[j / 2] = lo | (hi << 16);
           }
         }
+        }
       }
 
       // ---- P^T = exp2(S^T * c - LSE) = exp2(-(LSE - S^T * c)) ----
@@ -405,6 +427,23 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
       for (int h = 0; h < kCmpCols / 32; ++h) tmem_ld_32x32b_x32(tS + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[h * 32]));
       tmem_wait_ld();
+      if constexpr (kBias) {
+        if (p.bias_tma) {
+          // this thread's column (its key) of the staged bias tile, 32 query rows: 128-byte swizzled [query][64 keys]
+          // sub-tiles; the 32 lanes of a warp read 64 contiguous (permuted) bytes of one row - conflict free
+          mbar_wait(&bars[kBiasFull], it & 1);
+          const uint8_t* sub = sBias + (r >> 6) * (kBlk * 128) + (r & 7) * 2;
+          const uint32_t chunk = (r & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < kCmpCols; j += 2) {
+            const uint32_t q_lo = wg * kCmpCols + j, q_hi = q_lo + 1;
+            const uint32_t lo = *reinterpret_cast<const uint16_t*>(sub + sw128_offset(q_lo, chunk));
+            const uint32_t hi = *reinterpret_cast<const uint16_t*>(sub + sw128_offset(q_hi, chunk));
+            braw[j / 2] = lo | (hi << 16);
+          }
+          mbar_arrive(&bars[kBiasEmpty]);
+        }
+      }
       float2 pf[kPairs];  // probabilities, fp32, pairs of neighbouring query columns
 #pragma unroll
       for (int j4 = 0; j4 < kCmpCols / 4; ++j4) {
@@ -1085,7 +1124,8 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
                                      const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
                                      const DkdvParams& p, cudaStream_t stream) {
   auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kExtra>;
-  constexpr int smem = DkdvSmem<D>::kBytes;
+  constexpr int smem = DkdvSmem<D, (kExtra == 1 && D == 128) ? 2 : kQStages, kExtra == 1>::kBytes;
+  const CUtensorMap& tbias = p.bias_tma ? *p.bias_map : tq;  // placeholder when the bias is read through plain loads
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1095,7 +1135,7 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
     configured[dev] = true;
   }
   dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv * (kExtra == 3 ? p.kv_split : 1), p.B);
-  kernel<<<grid, kThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
+  kernel<<<grid, kThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, tbias, p);
   return cudaGetLastError();
 }
 

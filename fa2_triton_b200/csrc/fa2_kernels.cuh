@@ -155,6 +155,11 @@ struct DkdvParams {
   int64_t dv_strides[3];
   int max_ctas;           // > 0: cap on the persistent grid (the rest of the SMs is left to a concurrent kernel)
   BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
+  // kBias: a 16-bit bias whose rows TMA can address (16-byte aligned base and strides) is staged tile by tile through
+  // shared memory with `bias_map` ((Sk, Sq, 1 | Hq, 1 | B), box 64 x 128); otherwise every thread loads its values itself
+  int bias_tma;
+  const CUtensorMap* bias_map;          // host pointer, read by the launcher only
+  int bias_head_mul, bias_batch_mul;    // 0 for a broadcast dimension, else 1
   const int* seqlens;     // variable-length mode (one CTA per key block only), else nullptr
   const CUtensorMap* vmaps;
   int d_steps, d_cols;    // as in FwdParams: k-steps of the products that reduce over the head dim, N of those that span it
