@@ -247,6 +247,22 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
   p.d_cols = no_dtrim ? kernel_head_dim(D) : round_up(D, 16);
   if (int e = make_bias_view(&p.bias, bias, bias_dtype, bias_strides, dtype)) return e;
   p.bias_mul = 1.0f / softmax_scale;
+  CUtensorMap tbias;
+  if (bias && bias_dtype == dtype) {
+    // same rule as the dK / dV kernel's bias map below: [1 | B, 1 | Hq, Sq, Sk] seen as a [B', Sq, H', Sk] tensor, only if
+    // TMA can address it (16-byte aligned base, strides multiples of 8 elements); plain loads serve every other bias
+    const int Bb = bias_strides[0] ? B : 1, Hb = bias_strides[1] ? Hq : 1;
+    const int64_t bs[3] = {bias_strides[0], bias_strides[1], bias_strides[2]};
+    const bool ok = reinterpret_cast<uintptr_t>(bias) % 16 == 0 && bs[0] % 8 == 0 && bs[1] % 8 == 0 && bs[2] % 8 == 0 &&
+                    bs[2] > 0;
+    static const bool no_bias_tma = [] { const char* e = getenv("FA2_SM100_NO_BIAS_TMA"); return e && e[0] == '1'; }();
+    if (ok && !no_bias_tma && make_tmap_bshd(&tbias, bias, dtype, Bb, Sq, Hb, Sk, bs, 128, "bias") == 0) {
+      p.bias_tma = 1;
+      p.bias_map = &tbias;
+      p.bias_head_mul = Hb > 1 ? 1 : 0;
+      p.bias_batch_mul = Bb > 1 ? 1 : 0;
+    }
+  }
   p.dropout_p = dropout_p;
   p.inv_keep = 1.0f / (1.0f - dropout_p);
   p.seed_lo = static_cast<uint32_t>(dropout_seed & 0xffffffffull);

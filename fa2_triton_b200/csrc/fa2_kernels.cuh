@@ -40,6 +40,10 @@ struct FwdParams {
   // extras (kernel variant kExt; all zero otherwise)
   BiasView bias;
   float bias_mul;       // 1 / softmax_scale: the bias joins the raw scores, which are multiplied by scale_log2 later
+  // a 16-bit bias TMA can address: staged through shared memory with the map in bias_map ([B', Sq, H', Sk]; a broadcast
+  // batch / head dimension has extent 1 there, so its coordinate is multiplied by 0)
+  int bias_tma, bias_head_mul, bias_batch_mul;
+  const CUtensorMap* bias_map;  // host pointer, read by the launcher only
   float dropout_p;      // 0: no dropout
   float inv_keep;       // 1 / (1 - dropout_p)
   uint32_t seed_lo, seed_hi;

@@ -99,18 +99,23 @@ struct FwdSmem {
   static constexpr int kQOff = 0;
   static constexpr int kKOff = kQOff + 2 * kTileBytes;
   static constexpr int kVOff = kKOff + kStages * kTileBytes;
-  static constexpr int kBarOff = kVOff + kStages * kTileBytes;
-  // barriers: q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full[2]
-  static constexpr int kNumBars = 1 + 4 * kStages + 6;
+  // kExt (bias variant): 32 KB right behind the V ring (1024-byte aligned). A 16-bit bias that TMA can address lands there
+  // as one [128 rows x 64 keys] 128-byte-swizzled sub-tile per Q tile (2 x 16 KB); any other bias is staged by the softmax
+  // warps themselves - per warp 32 rows x 64 bytes, rows 80 bytes apart so that both the coalesced writes (8 rows x 64 B
+  // per instruction) and the row-per-lane 16-byte reads are conflict-free (8 x 2560 B, same region).
+  static constexpr int kBiasOff = kVOff + kStages * kTileBytes;
+  static constexpr int kBiasBufBytes = kBM * 128;
+  static constexpr int kStageOff = kBiasOff;
+  static constexpr int kStageRow = 80;
+  static constexpr int kStageWarpBytes = 32 * kStageRow;
+  static constexpr int kBarOff = kBiasOff + ((kExt && kHalves == 1) ? 2 * kBiasBufBytes : 0);
+  // barriers: q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full[2], bias_full[2], bias_empty[2]
+  static constexpr int kNumBars = 1 + 4 * kStages + 6 + 4;
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
   // row statistics exchanged between the kHalves threads of a row: [parity 2 x kind 2][tile 2][half 2][128 rows] fp32
   static constexpr int kXchgOff = kTmemSlotOff + 16;
-  // kExt: per softmax warp, a staging tile for the attention bias - 32 rows x 64 bytes, rows 80 bytes apart so that
-  // both the coalesced writes (8 rows x 64 B per instruction) and the row-per-lane 16-byte reads are conflict-free
-  static constexpr int kStageOff = (kXchgOff + 4 * 2 * 2 * kBM * 4 + 15) / 16 * 16;
-  static constexpr int kStageRow = 80;
-  static constexpr int kStageWarpBytes = 32 * kStageRow;
-  static constexpr int kBytes = kStageOff + ((kExt && kHalves == 1) ? (kSmxThreads / 32) * kStageWarpBytes : 0);
+  static constexpr int kBytes = kXchgOff + (kHalves == 2 ? 4 * 2 * 2 * kBM * 4 : 0);
+  static_assert(8 * kStageWarpBytes <= 2 * kBiasBufBytes, "the two bias layouts share one region");
   static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-byte alignment
   static_assert(kDynBytes <= 227 * 1024, "forward shared memory exceeds the 227 KB a CTA can have");
 };
@@ -125,13 +130,15 @@ __device__ __forceinline__ int num_kv_blocks(int row0, int Sq, int Sk, int causa
 
 }  // namespace
 
-// kExt: variants with an additive bias (bit 0) and / or forward dropout (bit 1), see extras.cuh; 0 = the plain kernel
+// kExt: variants with an additive bias (bit 0; with bit 2 it is staged through shared memory by TMA) and / or forward
+// dropout (bit 1), see extras.cuh; 0 = the plain kernel
 template <int D, bool kBf16, int kExt>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
-               const FwdParams p) {
+               const __grid_constant__ CUtensorMap tmap_bias, const FwdParams p) {
   using L = FwdSmem<D, (kExt & 1) != 0>;
+  constexpr bool kBiasTma = (kExt & 4) != 0;  // the bias travels through shared memory by TMA (with bit 0)
   constexpr int kStages = L::kStages;
   constexpr int kSub = D / 64;           // 64-column (128-byte) sub-tiles per row
   constexpr int kSubBytes = kBM * 128;   // one [128 x 64] 16-bit sub-tile
@@ -150,6 +157,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* s_full = v_empty + kStages;
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = p_full + 2;
+  [[maybe_unused]] uint64_t* bias_full = o_full + 2;
+  [[maybe_unused]] uint64_t* bias_empty = bias_full + 2;
+  [[maybe_unused]] uint8_t* sBias = smem + L::kBiasOff;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
   float* xchg = reinterpret_cast<float*>(smem + L::kXchgOff);
 
@@ -200,6 +210,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         mbar_init(&s_full[t], 1);
         mbar_init(&p_full[t], kTileSmxThreads);
         mbar_init(&o_full[t], 1);
+        mbar_init(&bias_full[t], 1);
+        mbar_init(&bias_empty[t], kTileSmxThreads);
       }
       fence_barrier_init();
     }
@@ -350,6 +362,25 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         static_cast<uint32_t>(p.Sk);
     (void)drop_row_off;
 
+    // ---- kExt bit 0, a 16-bit bias TMA can address (p.bias_tma): the tile's bias passes through shared memory in
+    // half-blocks of [128 rows x 64 keys] (16 KB, 128-byte swizzle, one buffer per Q tile). Half-block n = 2 i + h is
+    // requested by thread 0 of the tile as soon as all 128 rows of half-block n - 1 have been copied into registers
+    // (bias_empty), so the first half of block i + 1 travels during the softmax of block i and the second half of a
+    // block while its first half waits for the scores. A thread's row is 128 contiguous bytes whose 16-byte pieces sit
+    // at (piece ^ (row & 7)): the 8 rows of a quarter warp cover all 32 banks, no conflicts.
+    [[maybe_unused]] uint8_t* my_bias = sBias + t * L::kBiasBufBytes;
+    [[maybe_unused]] const int bias_h = head * p.bias_head_mul, bias_b = batch * p.bias_batch_mul;
+    [[maybe_unused]] auto bias_issue = [&](int n) {
+      mbar_arrive_expect_tx(&bias_full[t], L::kBiasBufBytes);
+      tma_load_4d(my_bias, &tmap_bias, &bias_full[t], n * 64, tile_row0, bias_h, bias_b);
+    };
+    if constexpr ((kExt & 1) && kHalves == 1) {
+      if (kBiasTma && nblk > 0 && r == 0) {
+        tma_prefetch_desc(&tmap_bias);
+        bias_issue(0);
+      }
+    }
+
     for (int i = 0; i < nblk; ++i) {
       if (r == 0 && half == 0) FA2_STAMP(t, i, 0);
       // ---- kExt: additive bias (src/forward/compute_row_blocks.py:48-54, 68-69) ----
@@ -433,9 +464,23 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if constexpr (kChunkCols == 32) tmem_st_32x32b_x32(tcol, sv); else tmem_st_32x32b_x16(tcol, sv);
         }
       };
+      // TMA-staged bias: copy this thread's 64 values of half-block n out of the tile's buffer and hand it back
+      uint4 bhalf[8], bhalf1[8];
+      [[maybe_unused]] auto bias_take = [&](int n, uint4* dst) {
+        mbar_wait(&bias_full[t], n & 1);
+        const uint8_t* rowp = my_bias + r * 128;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) dst[c8] = *reinterpret_cast<const uint4*>(rowp + ((c8 ^ (r & 7)) << 4));
+        mbar_arrive(&bias_empty[t]);
+        if (r == 0 && n + 1 < 2 * nblk) {
+          mbar_wait(&bias_empty[t], n & 1);
+          bias_issue(n + 1);
+        }
+      };
       if constexpr ((kExt & 1) && kHalves == 1) {
         if (p.bias.ptr != nullptr) {
-          if (p.bias.is_fp32) bias_fetch(std::integral_constant<int, 4>{}, 0);
+          if constexpr (kBiasTma) { bias_take(2 * i, bhalf); bias_take(2 * i + 1, bhalf1); }
+          else if (p.bias.is_fp32) bias_fetch(std::integral_constant<int, 4>{}, 0);
           else bias_fetch(std::integral_constant<int, 2>{}, 0);
         }
       }
@@ -464,7 +509,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if constexpr ((kExt & 1) != 0) {
         if (p.bias.ptr != nullptr) {
           if constexpr (kHalves == 1) {
-            if (p.bias.is_fp32) {  // 64 columns per pass: the second fetch is exposed (fp32 biases are the rare case)
+            if constexpr (kBiasTma) {
+              // added to the score registers below, without the round trip through tensor memory
+            } else if (p.bias.is_fp32) {  // 64 columns per pass: the second fetch is exposed (fp32 biases are the rare case)
               bias_apply(std::integral_constant<int, 4>{}, 0);
               bias_fetch(std::integral_constant<int, 4>{}, 1);
               bias_apply(std::integral_constant<int, 4>{}, 1);
@@ -487,7 +534,31 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
         for (int j = 0; j < kCols; ++j) s[j] = __uint_as_float(su[j / 32][j % 32]);
       };
-      load_scores();
+      bool scores_loaded = false;
+      if constexpr ((kExt & 1) && kHalves == 1) {
+        if constexpr (kBiasTma) {  // 64 scores at a time, so that at most 32 bias registers are live next to all 128 scores
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t su[2][32];
+            tmem_ld_32x32b_x32(tS + h * 64, su[0]);
+            tmem_ld_32x32b_x32(tS + h * 64 + 32, su[1]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const uint4 q4 = h == 0 ? bhalf[c8] : bhalf1[c8];
+              const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int jj = c8 * 8 + 2 * e;
+                s[h * 64 + jj] = fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] & 0xffffu)), p.bias_mul, __uint_as_float(su[jj / 32][jj % 32]));
+                s[h * 64 + jj + 1] = fmaf(bias_to_float<kBf16>(static_cast<uint16_t>(w[e] >> 16)), p.bias_mul, __uint_as_float(su[(jj + 1) / 32][(jj + 1) % 32]));
+              }
+            }
+          }
+          scores_loaded = true;
+        }
+      }
+      if (!scores_loaded) load_scores();
       if (r == 0 && half == 0) FA2_STAMP(t, i, 2);
 
       const int col0 = i * kBN + half * kCols;
@@ -507,7 +578,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // maximum first, rescale O, exponentiate). Results are identical to always taking the slow path; the maximum
       // pass leaves the softmax -> PV -> QK chain.
       bool done = false;
-      if (FA2_FWD_SPEC && i > 0 && !need_mask) {
+      if (FA2_FWD_SPEC && !(kExt & 1) && i > 0 && !need_mask) {
         const float neg_m = -m_ref;  // m_ref == -inf (row without any visible key so far): x = +inf forces the slow path
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
         float xm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -750,7 +821,8 @@ static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
     configured[dev] = true;
   }
   dim3 grid(p.n_pairs, p.Hq, p.B);
-  kernel<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, p);
+  const CUtensorMap& tbias = (kExt & 4) ? *p.bias_map : tq;  // placeholder when no bias goes through TMA
+  kernel<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, tbias, p);
   return cudaGetLastError();
 }
 
@@ -762,14 +834,16 @@ cudaError_t fetch_fwd_trace(long long* host, size_t n) {
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
-  const int ext = (p.bias.ptr != nullptr ? 1 : 0) | (p.dropout_p > 0.f ? 2 : 0);
+  const int ext = (p.bias.ptr != nullptr ? (p.bias_tma && p.bias_map && kHalves == 1 ? 5 : 1) : 0) | (p.dropout_p > 0.f ? 2 : 0);
 #define FA2_FWD_CASE(d, b)                                                                       \
   if (D == d && bf16 == b) {                                                                     \
     switch (ext) {                                                                               \
       case 0: return launch_fwd_t<d, b, 0>(tq, tk, tv, to, p, stream);                           \
       case 1: return launch_fwd_t<d, b, 1>(tq, tk, tv, to, p, stream);                           \
       case 2: return launch_fwd_t<d, b, 2>(tq, tk, tv, to, p, stream);                           \
-      default: return launch_fwd_t<d, b, 3>(tq, tk, tv, to, p, stream);                          \
+      case 3: return launch_fwd_t<d, b, 3>(tq, tk, tv, to, p, stream);                           \
+      case 5: return launch_fwd_t<d, b, 5>(tq, tk, tv, to, p, stream);                           \
+      default: return launch_fwd_t<d, b, 7>(tq, tk, tv, to, p, stream);                          \
     }                                                                                            \
   }
   FA2_FWD_CASE(128, true) FA2_FWD_CASE(128, false) FA2_FWD_CASE(64, true) FA2_FWD_CASE(64, false)
