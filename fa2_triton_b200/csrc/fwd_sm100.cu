@@ -468,10 +468,20 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       uint4 bhalf[8], bhalf1[8];
       [[maybe_unused]] auto bias_take = [&](int n, uint4* dst) {
         mbar_wait(&bias_full[t], n & 1);
-        const uint8_t* rowp = my_bias + r * 128;
+        const uint32_t rowp = smem_u32(my_bias) + r * 128;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) dst[c8] = *reinterpret_cast<const uint4*>(rowp + ((c8 ^ (r & 7)) << 4));
-        mbar_arrive(&bias_empty[t]);
+        for (int c8 = 0; c8 < 8; ++c8)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(dst[c8].x), "=r"(dst[c8].y), "=r"(dst[c8].z), "=r"(dst[c8].w)
+                       : "r"(rowp + ((c8 ^ (r & 7)) << 4)) : "memory");
+        // The buffer is overwritten by TMA once all 128 rows have arrived, so this thread's loads must have RETURNED by
+        // then - mbarrier.arrive alone does not wait for them (measured: without this a row now and then saw the next
+        // half-block, 1 run in 3 differed in a few rows at B=3, H=4, S=640). The arrive's address is made to depend on
+        // the loaded registers (a term that is always 0, which the compiler cannot know): cheaper than
+        // fence.proxy.async before the arrive (1.38 -> 1.78 ms non-causal with the fence).
+        uint32_t dep = (dst[0].x ^ dst[1].x ^ dst[2].x) ^ (dst[3].x ^ dst[4].x ^ dst[5].x) ^ (dst[6].x ^ dst[7].x);
+        dep &= static_cast<uint32_t>(p.bias_head_mul) >> 1;  // bias_head_mul is 0 or 1
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bias_empty[t]) + dep) : "memory");
         if (r == 0 && n + 1 < 2 * nblk) {
           mbar_wait(&bias_empty[t], n & 1);
           bias_issue(n + 1);

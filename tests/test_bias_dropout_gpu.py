@@ -85,6 +85,33 @@ def test_bias_fp32_and_strided():
     assert_close_16("O", out, er.flash_attn_reference(q, k, v, attn_bias=view))
 
 
+@pytest.mark.parametrize("dropout_p", [0.0, 0.1])
+@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,bias_bh", [
+    (2, 4, 1024, 1280, 128, True, (1, 1)),    # many key blocks: every parity of the half-block barriers
+    (2, 3, 700, 904, 64, False, (2, 3)),      # ragged tails in rows and keys, per-(batch, head) bias
+    (1, 2, 130, 136, 128, True, (1, 2)),      # second Q tile of the pair nearly empty
+    (2, 2, 1, 256, 64, False, (2, 1)),        # a single query row
+])
+def test_bias_staged_by_tma_equals_bias_through_plain_loads(B, H, Sq, Sk, D, causal, bias_bh, dropout_p):
+    # A 16-bit bias TMA can address (16-byte aligned base and rows) is staged through shared memory
+    # (fa2_fwd_kernel<.., kExt = 5 / 7>); any other takes the warps' own loads (kExt = 1 / 3). Same values, one element
+    # of misalignment: O and LSE must not differ in a single bit.
+    q, k, v, _ = generate_test_data(B, Sq, Sk, H, H, D, torch.bfloat16, DEV, seed=Sq + D)
+    Bb, Hb = bias_bh
+    aligned = make_bias((Bb, Hb, Sq, Sk), torch.bfloat16, seed=7)
+    big = torch.zeros(Bb, Hb, Sq, Sk + 8, dtype=torch.bfloat16, device=DEV)
+    view = big[..., 1:1 + Sk]
+    view.copy_(aligned)
+    assert aligned.data_ptr() % 16 == 0 and view.data_ptr() % 16 != 0
+    a = fa2._flash_attn_forward(q, k, v, None, aligned, dropout_p, causal, None, 1234)
+    b = fa2._flash_attn_forward(q, k, v, None, view, dropout_p, causal, None, 1234)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(a[1], b[1])
+    if dropout_p == 0.0:
+        assert_close_16("O", a[0], er.flash_attn_reference(q, k, v, attn_bias=aligned, causal=causal))
+
+
 def test_bias_minus_inf_acts_as_a_mask():
     run_bias_case(2, 256, 384, 2, 2, 128, False, torch.bfloat16, (1, 1, 256, 384), with_inf=True)
     run_bias_case(1, 200, 200, 2, 1, 64, True, torch.float16, (1, 2, 200, 200), with_inf=True, det=1)
