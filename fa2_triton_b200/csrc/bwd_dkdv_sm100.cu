@@ -441,7 +441,14 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const uint32_t hi = *reinterpret_cast<const uint16_t*>(sub + sw128_offset(q_hi, chunk));
             braw[j / 2] = lo | (hi << 16);
           }
-          mbar_arrive(&bars[kBiasEmpty]);
+          // TMA overwrites the tile once every reader has arrived, so the loads above must have RETURNED before this
+          // thread arrives (mbarrier.arrive does not wait for them; the forward kernel's bias buffer showed the race,
+          // fwd_sm100.cu): the arrive's address depends on the loaded registers through a term that is always 0
+          uint32_t dep = 0;
+#pragma unroll
+          for (int j = 0; j < kCmpCols / 2; ++j) dep ^= braw[j];
+          dep &= static_cast<uint32_t>(p.bias_head_mul) >> 1;  // bias_head_mul is 0 or 1
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[kBiasEmpty]) + dep) : "memory");
         }
       }
       float2 pf[kPairs];  // probabilities, fp32, pairs of neighbouring query columns

@@ -1,5 +1,10 @@
+"""Bit-repeatability of the bias paths (forward + backward 40 times, forward alone 400 times): how the race between a
+thread's reads of the TMA-staged bias buffer and the next TMA write into it was found and its fix checked.
+Usage: python scripts/bias_repeat.py"""
 import sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import fa2_triton_b200 as fa2
 from fa2_test_utils import generate_test_data
 DEV = "cuda:0"
