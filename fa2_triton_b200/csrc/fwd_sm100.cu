@@ -92,19 +92,23 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between
 #define FA2_FWD_SPEC 0
 #endif
 
-template <int D, bool kExt = false>
+template <int D, bool kExt = false, bool kBiasTma = false>
 struct FwdSmem {
-  static constexpr int kStages = (D == 128) ? 2 : 4;
+  static constexpr int kStages = (D == 128) ? 2 : 4;  // K ring
+  // The TMA-staged bias needs a whole [128 x 128] block per Q tile in flight (64 KB): at head dim 128 it takes the second
+  // V stage (V(i + 1) is requested when P V(i) of both tiles has completed and needed about half a block period later)
+  static constexpr int kVStages = (kBiasTma && D == 128) ? 1 : kStages;
   static constexpr int kTileBytes = kBM * D * 2;  // Q, K and V tiles all have 128 rows
   static constexpr int kQOff = 0;
   static constexpr int kKOff = kQOff + 2 * kTileBytes;
   static constexpr int kVOff = kKOff + kStages * kTileBytes;
-  // kExt (bias variant): 32 KB right behind the V ring (1024-byte aligned). A 16-bit bias that TMA can address lands there
-  // as one [128 rows x 64 keys] 128-byte-swizzled sub-tile per Q tile (2 x 16 KB); any other bias is staged by the softmax
-  // warps themselves - per warp 32 rows x 64 bytes, rows 80 bytes apart so that both the coalesced writes (8 rows x 64 B
-  // per instruction) and the row-per-lane 16-byte reads are conflict-free (8 x 2560 B, same region).
-  static constexpr int kBiasOff = kVOff + kStages * kTileBytes;
-  static constexpr int kBiasBufBytes = kBM * 128;
+  // kExt (bias variants): a region right behind the V ring (1024-byte aligned). A 16-bit bias that TMA can address lands
+  // there as two [128 rows x 64 keys] 128-byte-swizzled sub-tiles per Q tile and block (2 x 32 KB); any other bias is
+  // staged by the softmax warps themselves - per warp 32 rows x 64 bytes, rows 80 bytes apart so that both the coalesced
+  // writes (8 rows x 64 B per instruction) and the row-per-lane 16-byte reads are conflict-free (8 x 2560 B in 32 KB).
+  static constexpr int kBiasOff = kVOff + kVStages * kTileBytes;
+  static constexpr int kBiasSubBytes = kBM * 128;
+  static constexpr int kBiasBufBytes = (kBiasTma ? 2 : 1) * kBiasSubBytes;
   static constexpr int kStageOff = kBiasOff;
   static constexpr int kStageRow = 80;
   static constexpr int kStageWarpBytes = 32 * kStageRow;
@@ -137,8 +141,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                const __grid_constant__ CUtensorMap tmap_bias, const FwdParams p) {
-  using L = FwdSmem<D, (kExt & 1) != 0>;
-  constexpr bool kBiasTma = (kExt & 4) != 0;  // the bias travels through shared memory by TMA (with bit 0)
+  constexpr bool kBiasTma = (kExt & 4) != 0;
+  using L = FwdSmem<D, (kExt & 1) != 0, kBiasTma>;
+  constexpr int kVStages = L::kVStages;  // the bias travels through shared memory by TMA (with bit 0)
   constexpr int kStages = L::kStages;
   constexpr int kSub = D / 64;           // 64-column (128-byte) sub-tiles per row
   constexpr int kSubBytes = kBM * 128;   // one [128 x 64] 16-bit sub-tile
@@ -246,10 +251,12 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         mbar_arrive_expect_tx(&k_full[s], L::kTileBytes);
         for (int j = 0; j < kSub; ++j)
           tma_load_4d(sK + s * L::kTileBytes + j * kSubBytes, mk, &k_full[s], j * 64, i * kBN, head_kv, bc);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], L::kTileBytes);
+        const int sv = i % kVStages;
+        const uint32_t phv = (i / kVStages) & 1;
+        mbar_wait(&v_empty[sv], phv ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], L::kTileBytes);
         for (int j = 0; j < kSub; ++j)
-          tma_load_4d(sV + s * L::kTileBytes + j * kSubBytes, mv, &v_full[s], j * 64, i * kBN, head_kv, bc);
+          tma_load_4d(sV + sv * L::kTileBytes + j * kSubBytes, mv, &v_full[sv], j * 64, i * kBN, head_kv, bc);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -303,7 +310,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int sn = (i + 1) % kStages;
         const uint32_t phn = ((i + 1) / kStages) & 1;
         bool next_k_ready = false;
-        mbar_wait(&v_full[s], ph);
+        const int sv = i % kVStages;
+        mbar_wait(&v_full[sv], (i / kVStages) & 1);
         if (i + 1 < nblk_max) {  // K(i+1) is usually there long before P(i): take that wait off the P -> S chain
           mbar_wait(&k_full[sn], phn);
           next_k_ready = true;
@@ -314,7 +322,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             mbar_wait(&p_full[t], i & 1);
             tcgen05_fence_after();
             FA2_STAMP(2, i, t * 4 + 0);
-            issue_pv(t, s, i > 0);
+            issue_pv(t, sv, i > 0);
             FA2_STAMP(2, i, t * 4 + 1);
             if (i + 1 < nblk[t]) {
               if (!next_k_ready) {
@@ -331,7 +339,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
           }
         }
-        umma_commit(&v_empty[s]);
+        umma_commit(&v_empty[sv]);
         if (i + 1 < nblk_max) umma_commit(&k_empty[sn]);
       }
     }
@@ -362,17 +370,19 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         static_cast<uint32_t>(p.Sk);
     (void)drop_row_off;
 
-    // ---- kExt bit 0, a 16-bit bias TMA can address (p.bias_tma): the tile's bias passes through shared memory in
-    // half-blocks of [128 rows x 64 keys] (16 KB, 128-byte swizzle, one buffer per Q tile). Half-block n = 2 i + h is
-    // requested by thread 0 of the tile as soon as all 128 rows of half-block n - 1 have been copied into registers
-    // (bias_empty), so the first half of block i + 1 travels during the softmax of block i and the second half of a
-    // block while its first half waits for the scores. A thread's row is 128 contiguous bytes whose 16-byte pieces sit
-    // at (piece ^ (row & 7)): the 8 rows of a quarter warp cover all 32 banks, no conflicts.
+    // ---- kExt bits 0 + 2, a 16-bit bias TMA can address: the tile's bias passes through shared memory one
+    // [128 rows x 128 keys] block at a time (two 128-byte-swizzled sub-tiles of 64 keys, one 32 KB buffer per Q tile).
+    // Block i + 1 is requested by thread 0 of the tile as soon as all 128 rows of block i sit in registers (bias_empty),
+    // i.e. before the scores of block i have even arrived, and travels during that block's softmax. (With 16 KB per tile
+    // - half a block in flight - every block exposed one TMA round trip: 1.17 ms instead of the plain forward's 0.57.)
+    // A thread's row is 2 x 128 contiguous bytes whose 16-byte pieces sit at (piece ^ (row & 7)): the 8 rows of a
+    // quarter warp cover all 32 banks, no conflicts.
     [[maybe_unused]] uint8_t* my_bias = sBias + t * L::kBiasBufBytes;
     [[maybe_unused]] const int bias_h = head * p.bias_head_mul, bias_b = batch * p.bias_batch_mul;
-    [[maybe_unused]] auto bias_issue = [&](int n) {
-      mbar_arrive_expect_tx(&bias_full[t], L::kBiasBufBytes);
-      tma_load_4d(my_bias, &tmap_bias, &bias_full[t], n * 64, tile_row0, bias_h, bias_b);
+    [[maybe_unused]] auto bias_issue = [&](int blk) {
+      mbar_arrive_expect_tx(&bias_full[t], 2 * L::kBiasSubBytes);
+      for (int j = 0; j < 2; ++j)
+        tma_load_4d(my_bias + j * L::kBiasSubBytes, &tmap_bias, &bias_full[t], blk * kBN + j * 64, tile_row0, bias_h, bias_b);
     };
     if constexpr ((kExt & 1) && kHalves == 1) {
       if (kBiasTma && nblk > 0 && r == 0) {
@@ -464,32 +474,36 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if constexpr (kChunkCols == 32) tmem_st_32x32b_x32(tcol, sv); else tmem_st_32x32b_x16(tcol, sv);
         }
       };
-      // TMA-staged bias: copy this thread's 64 values of half-block n out of the tile's buffer and hand it back
+      // TMA-staged bias: copy this thread's 128 values of block i out of the tile's buffer and hand it back
       uint4 bhalf[8], bhalf1[8];
-      [[maybe_unused]] auto bias_take = [&](int n, uint4* dst) {
-        mbar_wait(&bias_full[t], n & 1);
+      [[maybe_unused]] auto bias_take = [&]() {
+        mbar_wait(&bias_full[t], i & 1);
         const uint32_t rowp = smem_u32(my_bias) + r * 128;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8)
+        for (int c8 = 0; c8 < 16; ++c8) {
+          uint4& d = c8 < 8 ? bhalf[c8] : bhalf1[c8 - 8];
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(dst[c8].x), "=r"(dst[c8].y), "=r"(dst[c8].z), "=r"(dst[c8].w)
-                       : "r"(rowp + ((c8 ^ (r & 7)) << 4)) : "memory");
+                       : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w)
+                       : "r"(rowp + (c8 / 8) * L::kBiasSubBytes + (((c8 % 8) ^ (r & 7)) << 4)) : "memory");
+        }
         // The buffer is overwritten by TMA once all 128 rows have arrived, so this thread's loads must have RETURNED by
         // then - mbarrier.arrive alone does not wait for them (measured: without this a row now and then saw the next
-        // half-block, 1 run in 3 differed in a few rows at B=3, H=4, S=640). The arrive's address is made to depend on
-        // the loaded registers (a term that is always 0, which the compiler cannot know): cheaper than
-        // fence.proxy.async before the arrive (1.38 -> 1.78 ms non-causal with the fence).
-        uint32_t dep = (dst[0].x ^ dst[1].x ^ dst[2].x) ^ (dst[3].x ^ dst[4].x ^ dst[5].x) ^ (dst[6].x ^ dst[7].x);
+        // tile, 1 run in 3 differed in a few rows at B=3, H=4, S=640). The arrive's address is made to depend on the
+        // loaded registers (a term that is always 0, which the compiler cannot know); fence.proxy.async before the
+        // arrive works as well.
+        uint32_t dep = 0;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) dep ^= bhalf[c8].x ^ bhalf1[c8].x;
         dep &= static_cast<uint32_t>(p.bias_head_mul) >> 1;  // bias_head_mul is 0 or 1
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bias_empty[t]) + dep) : "memory");
-        if (r == 0 && n + 1 < 2 * nblk) {
-          mbar_wait(&bias_empty[t], n & 1);
-          bias_issue(n + 1);
+        if (r == 0 && i + 1 < nblk) {
+          mbar_wait(&bias_empty[t], i & 1);
+          bias_issue(i + 1);
         }
       };
       if constexpr ((kExt & 1) && kHalves == 1) {
         if (p.bias.ptr != nullptr) {
-          if constexpr (kBiasTma) { bias_take(2 * i, bhalf); bias_take(2 * i + 1, bhalf1); }
+          if constexpr (kBiasTma) bias_take();
           else if (p.bias.is_fp32) bias_fetch(std::integral_constant<int, 4>{}, 0);
           else bias_fetch(std::integral_constant<int, 2>{}, 0);
         }
@@ -821,7 +835,7 @@ template <int D, bool kBf16, int kExt>
 static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                 const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
   auto kernel = fa2_fwd_kernel<D, kBf16, kExt>;
-  constexpr int smem = FwdSmem<D, (kExt & 1) != 0>::kDynBytes;
+  constexpr int smem = FwdSmem<D, (kExt & 1) != 0, (kExt & 4) != 0>::kDynBytes;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
