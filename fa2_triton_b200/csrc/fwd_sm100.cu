@@ -305,8 +305,6 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       umma_commit(&k_empty[0]);
 
       for (int i = 0; i < nblk_max; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
         const int sn = (i + 1) % kStages;
         const uint32_t phn = ((i + 1) / kStages) & 1;
         bool next_k_ready = false;
