@@ -229,7 +229,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   // This CTA allocated all 512 columns, so the allocation starts at lane 0 / column 0. Using the literal 0 (after
   // checking it) keeps every tcgen05 address provably warp-uniform: ptxas then feeds UTCHMMA / LDTM / STTM from
   // uniform registers directly instead of wrapping each one in an ELECT + R2UR.BROADCAST "waterfall" (which cost
-  // ~100 issue cycles per MMA and made the single issuing thread the bottleneck - profiles/r01_fwd_hot.txt).
+  // ~100 issue cycles per MMA and made the single issuing thread the bottleneck - DESIGN.md section 4;
+  // profiles/r01d_fa2_fwd_kernel_opcodes.txt shows what is left of R2UR).
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
