@@ -10,8 +10,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .forward import (SUPPORTED_HEAD_DIMS, _stream_ptr, check_bias, device_sequence_lengths, encode_dtype, handle_dropout,
-                      pad_last, padded_head_dim, runs_natively, sequence_lengths, varlen_in_kernel)
+from .forward import (FUSED_HEAD_DIMS, _stream_ptr, check_bias, device_sequence_lengths, encode_dtype, handle_dropout,
+                      kernel_addressable, pad_last, padded_head_dim, runs_natively, sequence_lengths, varlen_in_kernel)
 
 # Process-wide default for how dQ contributions are summed.
 #   True     : deterministic - dQ comes from its own kernel, one CTA per query block walking the key blocks in a
@@ -118,6 +118,9 @@ def _flash_attn_backward(
     (``ctx.needs_input_grad``); the skipped gradients are returned as ``None``."""
     handle_dropout(dropout_p, dropout_seed, is_forward=False)  # raises NotImplementedError under dropout, like src/utils.py:87-88
     dO = dO.contiguous() if dO.stride(-1) != 1 else dO
+    if q.is_cuda and runs_natively(q.shape[-1]):
+        # what TMA cannot address (expanded tensors, e.g. the dO of out.sum(); unaligned views) is materialised
+        dO, q, k, v, o = (kernel_addressable(t) for t in (dO, q, k, v, o))
     if attention_mask is not None:
         assert bias is None, "Attention mask is not supported along with attention bias. Just use bias instead."
         # Variable-length mode (src/backward/caller.py:29-79, 168-176): per-sequence views instead of pack / unpack;
@@ -147,9 +150,11 @@ def _flash_attn_backward(
     fused_req = bias is None and (det_req is False or (not isinstance(det_req, bool) and det_req in (0, 2)))
     # zero-padded copies only for head dims TMA cannot address (not a multiple of 8) and for the fused kernel, whose dQ
     # accumulator layout exists for 64 and 128 only
-    if not runs_natively(q.shape[-1]) or (fused_req and q.shape[-1] not in SUPPORTED_HEAD_DIMS):
+    if fused_req and q.shape[-1] > FUSED_HEAD_DIMS[-1]:
+        fused_req, deterministic = False, True  # the fused kernel stops at head dim 128: the deterministic kernels serve it
+    if not runs_natively(q.shape[-1]) or (fused_req and q.shape[-1] not in FUSED_HEAD_DIMS):
         head_dim = q.shape[-1]
-        d = padded_head_dim(head_dim)
+        d = padded_head_dim(head_dim, FUSED_HEAD_DIMS if fused_req else None)
         scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
         part = _flash_attn_backward(pad_last(dO, d), pad_last(q, d), pad_last(k, d), pad_last(v, d), bias, None,
                                     pad_last(o, d), lse, dropout_p, causal, scale, dropout_seed, deterministic,

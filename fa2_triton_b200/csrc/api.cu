@@ -52,15 +52,21 @@ bool is_16bit(int dtype) { return dtype == FA2_DTYPE_FP16 || dtype == FA2_DTYPE_
 // 128-byte swizzle, zero fill for out-of-bounds rows.
 int make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype, int B, int S, int H, int D, const int64_t strides[3],
                    int box_rows, const char* name) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(FA2_E_NO_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   if (!ptr) return fail(FA2_E_NULL_POINTER, "%s: null pointer", name);
   if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0) return fail(FA2_E_BAD_ALIGNMENT, "%s: base not 16-byte aligned", name);
+  const int extent[3] = {B, H, S};  // strides[] = (batch, head, seq)
   for (int i = 0; i < 3; ++i) {
     if (strides[i] < 0 || (strides[i] * 2) % 16 != 0)
       return fail(FA2_E_BAD_ALIGNMENT, "%s: stride[%d]=%lld elements is not a non-negative multiple of 8", name, i,
                   static_cast<long long>(strides[i]));
+    // A zero stride is only meaningful for a dimension of extent 1 (torch reports arbitrary strides there). An expanded
+    // (broadcast) tensor must be materialised by the caller: TMA cannot address it and the rows would alias.
+    if (strides[i] == 0 && extent[i] > 1)
+      return fail(FA2_E_BAD_SHAPE, "%s: stride[%d] is 0 for a dimension of extent %d (expanded tensor): pass a "
+                                   "materialised (contiguous) tensor", name, i, extent[i]);
   }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(FA2_E_NO_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(H),
                               static_cast<cuuint64_t>(B)};
   // a size-1 dimension may carry a zero stride in torch; TMA wants something positive and 16-byte granular
@@ -77,8 +83,8 @@ int make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype, int B, int S, i
 
 int check_common(int B, int Hq, int Hkv, int Sq, int Sk, int D, int dtype) {
   if (!is_16bit(dtype)) return fail(FA2_E_UNSUPPORTED_DTYPE, "dtype code %d: only 16 (fp16) and 17 (bf16) are supported", dtype);
-  if (D < 8 || D > 128 || D % 8 != 0)
-    return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: this build supports multiples of 8 up to 128", D);
+  if (D < 8 || D > 256 || D % 8 != 0)
+    return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: this build supports multiples of 8 up to 256", D);
   if (B < 1 || Hq < 1 || Hkv < 1 || Sq < 1 || Sk < 1) return fail(FA2_E_BAD_SHAPE, "non-positive dimension");
   if (Hq % Hkv != 0) return fail(FA2_E_BAD_SHAPE, "nheads_q = %d is not divisible by nheads_kv = %d", Hq, Hkv);
   if (Hq > 65535 || B > 65535) return fail(FA2_E_BAD_SHAPE, "batch and head counts must fit a grid dimension");
@@ -154,9 +160,9 @@ int make_bias_view(fa2::BiasView* view, const void* bias, int bias_dtype, const 
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// The kernels are instantiated for head dims 64 and 128. Any multiple of 8 below runs in the next instantiation: the
+// The kernels are instantiated for head dims 64, 128 and 256. Any multiple of 8 below runs in the next instantiation: the
 // tensor maps carry the real head dim, so TMA zero-fills the missing columns on load and clips them on store.
-int kernel_head_dim(int D) { return D <= 64 ? 64 : 128; }
+int kernel_head_dim(int D) { return D <= 64 ? 64 : D <= 128 ? 128 : 256; }
 
 int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int Sq,
              int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
@@ -231,9 +237,14 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
   if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
   CUtensorMap tq, tk, tv, to;
   if (int e = make_tmap_bshd(&tq, q, dtype, B, Sq, Hq, D, q_strides, 128, "q")) return e;
-  if (int e = make_tmap_bshd(&tk, k, dtype, B, Sk, Hkv, D, k_strides, 128, "k")) return e;
-  if (int e = make_tmap_bshd(&tv, v, dtype, B, Sk, Hkv, D, v_strides, 128, "v")) return e;
+  // head dims above 128: the forward stages K / V in tiles of 64 keys (fwd2_sm100.cu)
+  const int kv_box_rows = kernel_head_dim(D) == 256 ? 64 : 128;
+  if (int e = make_tmap_bshd(&tk, k, dtype, B, Sk, Hkv, D, k_strides, kv_box_rows, "k")) return e;
+  if (int e = make_tmap_bshd(&tv, v, dtype, B, Sk, Hkv, D, v_strides, kv_box_rows, "v")) return e;
   if (int e = make_tmap_bshd(&to, o, dtype, B, Sq, Hq, D, o_strides, 128, "o")) return e;
+  if (D > 128 && dropout_p > 0.f)
+    return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: forward dropout is built for head dims up to 128", D);
+  if (D > 128 && seqlens && bias) return fail(FA2_E_BAD_SHAPE, "bias together with variable-length mode");
   fa2::FwdParams p{};
   p.lse = lse;
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk;
@@ -248,7 +259,7 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
   if (int e = make_bias_view(&p.bias, bias, bias_dtype, bias_strides, dtype)) return e;
   p.bias_mul = 1.0f / softmax_scale;
   CUtensorMap tbias;
-  if (bias && bias_dtype == dtype) {
+  if (bias && bias_dtype == dtype && D <= 128) {
     // same rule as the dK / dV kernel's bias map below: [1 | B, 1 | Hq, Sq, Sk] seen as a [B', Sq, H', Sk] tensor, only if
     // TMA can address it (16-byte aligned base, strides multiples of 8 elements); plain loads serve every other bias
     const int Bb = bias_strides[0] ? B : 1, Hb = bias_strides[1] ? Hq : 1;
@@ -417,6 +428,7 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
   fa2::BiasView bias_view{};
   if (int e = make_bias_view(&bias_view, bias, bias_dtype, bias_strides, dtype)) return e;
   const int Dk = kernel_head_dim(D);
+  if (D > 128) return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: the backward is built for head dims up to 128", D);
   if (D != Dk && (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED))
     return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: the fused (atomic / ticket-ordered) backward needs 64 or 128; "
                                             "the deterministic modes take any multiple of 8 up to 128", D);

@@ -5,9 +5,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <vector>
+
 #include "extras.cuh"
 
 namespace fa2 {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); safe to call from several host threads
+template <auto Kernel>
+inline cudaError_t ensure_dynamic_smem(int bytes) {
+  static std::mutex mu;
+  static std::vector<char> done;  // indexed by device ordinal
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> guard(mu);
+  if (dev < static_cast<int>(done.size()) && done[dev]) return cudaSuccess;
+  if (cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); e != cudaSuccess) return e;
+  if (static_cast<int>(done.size()) <= dev) done.resize(dev + 1, 0);
+  done[dev] = 1;
+  return cudaSuccess;
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward (fwd_sm100.cu)
@@ -56,6 +74,10 @@ struct FwdParams {
 
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const CUtensorMap& to, const FwdParams& p, cudaStream_t stream);
+// fwd2_sm100.cu: the plain forward (no bias, no dropout) with double-buffered 64-key half-blocks, head-dim instantiations
+// 64 / 128 / 256 (256 also with a bias). The K / V tensor maps must have box rows 128 (D <= 128) or 64 (D = 256).
+cudaError_t launch_fwd2(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                        const CUtensorMap& to, const FwdParams& p, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // backward (bwd_sm100.cu)

@@ -1,21 +1,17 @@
-// FlashAttention-2 forward for sm_100a (B200): TMA -> smem ring -> tcgen05.mma (S = Q K^T, O += P V) with
-// accumulators in tensor memory, two 128-row Q tiles per CTA whose softmax warpgroups ping-pong against
-// the single MMA-issuing warp.
+// FlashAttention-2 forward for sm_100a (B200), the variants with an additive bias and / or forward dropout
+// (SURVEY.md section 8f rank 4). The plain forward lives in fwd2_sm100.cu; this translation unit keeps the first-generation
+// pipeline - TMA -> smem ring -> tcgen05.mma (S = Q K^T, O += P V) with accumulators in tensor memory, two 128-row Q
+// tiles per CTA whose softmax warpgroups ping-pong against the single MMA-issuing warp - because the bias staging
+// (one [128 x 128] block per tile through shared memory by TMA) and the dropout draw are built around 128-key blocks.
 //
 // Replaces the reference's `_fwd_kernel` (src/forward/kernel.py:61-291) + `compute_row_block`
-// (src/forward/compute_row_blocks.py:8-103). Same arithmetic contract:
-//   S = Q K^T (fp32 acc); masked where col >= Sk or (causal) col > row + Sk - Sq;
+// (src/forward/compute_row_blocks.py:8-103) for `BIAS_ON` / `USE_DROPOUT`. Same arithmetic contract:
+//   S = Q K^T (fp32 acc) + bias / scale; masked where col >= Sk or (causal) col > row + Sk - Sq;
 //   log2-domain online softmax with c = softmax_scale * log2(e); P rounded to the input dtype before PV;
 //   O = (P V) / l in the input dtype;  LSE2 = m + log2(l) in fp32 (src/forward/kernel.py:119,259-272).
 //
-// CTA = 2 * kHalves softmax warpgroups + one issue warpgroup (kHalves = FA2_FWD_HALVES, 1 or 2):
-//   softmax warpgroup (t, h): Q tile t, key columns [h * 128 / kHalves, ...) of every block; thread = query row
-//                             (TMEM lane == row). With kHalves = 2 the two threads of a row exchange their block
-//                             maxima through shared memory (one named barrier per block) and keep partial row sums.
-//                             Four softmax warps per scheduler instead of two: the row's 128 exponentials are the
-//                             dependent chain softmax -> PV -> QK(next) of a tile is waiting for, and a lone warp
-//                             only keeps the MUFU ~2/3 busy (measured T_softmax 2100 cycles -> see DESIGN.md).
-//   issue warpgroup: warp 0 MMA issuer (one elected lane), warp 1 TMA producer (one elected lane), 2 idle warps
+// CTA = 2 softmax warpgroups (one per Q tile; thread = query row = TMEM lane) + one issue warpgroup
+//   (warp 0 MMA issuer, warp 1 TMA producer, 2 idle warps).
 // TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,256+D) | O1 [256+D,256+2D).
 //   P_t (16-bit) overwrites the head of the S_t columns of the thread that wrote it, once it has read its row.
 #include <type_traits>
@@ -25,72 +21,19 @@
 
 namespace fa2 {
 
-#ifdef FA2_TRACE
-// Debug build only (make TRACE=1): clock64() stamps of one CTA's pipeline events, [role][iteration][event].
-__device__ long long g_fwd_trace[3 * 64 * 8];
-#define FA2_STAMP(role, it, ev)                                                                          \
-  do {                                                                                                   \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 64)                              \
-      g_fwd_trace[((role) * 64 + (it)) * 8 + (ev)] = clock64();                                          \
-  } while (0)
-#else
-#define FA2_STAMP(role, it, ev) do { } while (0)
-#endif
-
 namespace {
 
 constexpr int kBM = 128;  // query rows per tile (= TMEM lanes)
 constexpr int kBN = 128;  // key rows per block
-// Measured on B200 (B=4, H=32, S=4096, D=128 causal; same box, same call): 1 thread per row 0.566 ms, + speculative
-// exponentials 0.567, 2 threads per row 0.574, 2 threads + speculative 0.643, + a quarter of the exponentials on the FMA
-// pipes 0.637. Shortening the softmax chain does not move the kernel: with ~1 kW drawn it runs at the power cap (SM clock
-// 1.55-1.75 GHz instead of 1.965), so what counts is work per step, not bubbles - the leanest variant is the default.
-#ifndef FA2_FWD_HALVES
-#define FA2_FWD_HALVES 1
-#endif
-constexpr int kHalves = FA2_FWD_HALVES;          // softmax threads per query row
-constexpr int kCols = kBN / kHalves;             // key columns per softmax thread
-constexpr int kSmxThreads = 2 * kHalves * 128;   // softmax threads per CTA
-constexpr int kTileSmxThreads = kHalves * 128;   // ... per Q tile
+constexpr int kCols = kBN;                       // key columns per softmax thread
+constexpr int kSmxThreads = 2 * 128;             // softmax threads per CTA
+constexpr int kTileSmxThreads = 128;             // ... per Q tile
 constexpr int kFwdThreads = kSmxThreads + 128;
 constexpr int kMmaWarp = kSmxThreads / 32, kTmaWarp = kMmaWarp + 1;
 // register pools (setmaxnreg): 384 threads x 168 = 64512 = 2 x 128 x 208 + 128 x 88
-//                              640 threads x  96 = 61440 = 4 x 128 x 104 + 128 x 64
-constexpr int kRegsSmx = kHalves == 2 ? 104 : 208;
-constexpr int kRegsIssue = kHalves == 2 ? 64 : 88;
+constexpr int kRegsSmx = 208;
+constexpr int kRegsIssue = 88;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays <= 2^8 between rescales
-// Of every FA2_FWD_EMUL_DEN probabilities, FA2_FWD_EMUL_NUM are exponentiated on the FMA pipes (ex2_emul) and the rest
-// on the MUFU. Measured issue costs per warp instruction and scheduler (scripts/micro/pipe_rates.cu): MUFU.EX2 8 cycles,
-// FFMA / FADD / IMAD 1, FMNMX / F2FP 2 - an emulated exponential is 8 instructions, so about a quarter of them
-// would balance the pipes on paper. Measured on B200 (B=4,H=32,S=4096,D=128 causal): 0/4 -> 0.567 ms, 1/4 -> 0.591,
-// 1/3 -> 0.616, 1/2 -> 0.651: with one softmax warp per scheduler the phase is latency-bound, not MUFU-bound, and the
-// extra dependent instructions cost more than the MUFU slots they free. Default: off.
-#ifndef FA2_FWD_EMUL_NUM
-#define FA2_FWD_EMUL_NUM (D == 64 ? 1 : 0)  // evaluated inside the kernel template
-#endif
-#ifndef FA2_FWD_EMUL_DEN
-#define FA2_FWD_EMUL_DEN 4
-#endif
-// Packed flavour (whole pairs through ex2_emul2, f32x2 arithmetic). Measured, same box and call: D = 64 (S = 16384,
-// non-causal, where the 16384 exponentials of a tile take twice as long on the MUFU as its two products on the tensor
-// pipe): 1 of 4 pairs 3.15 -> 2.92 ms, 2 of 4 3.21; D = 128 (S = 4096 causal): 0.560 -> 0.566 / 0.561. Hence the
-// default: a quarter of the pairs at D = 64, none at D = 128.
-// Energy / time ablations for DESIGN.md (results are WRONG on purpose, never shipped): 1 = exponentials replaced by a
-// move, 2 = additionally no maximum pass / rescale, 3 = no softmax arithmetic at all (P = rounded raw scores, no row sum)
-#ifndef FA2_FWD_ABLATE
-#define FA2_FWD_ABLATE 0
-#endif
-// Experiment: both exponentials of a pair in one MUFU.EX2.F16x2 (the arguments and results pass through fp16)
-#ifndef FA2_FWD_EX2_F16
-#define FA2_FWD_EX2_F16 0
-#endif
-#ifndef FA2_FWD_EMUL_PACKED
-#define FA2_FWD_EMUL_PACKED 1
-#endif
-// Speculative exponentials against the previous reference maximum (see the softmax loop). Off: no gain (see above).
-#ifndef FA2_FWD_SPEC
-#define FA2_FWD_SPEC 0
-#endif
 
 template <int D, bool kExt = false, bool kBiasTma = false>
 struct FwdSmem {
@@ -112,13 +55,11 @@ struct FwdSmem {
   static constexpr int kStageOff = kBiasOff;
   static constexpr int kStageRow = 80;
   static constexpr int kStageWarpBytes = 32 * kStageRow;
-  static constexpr int kBarOff = kBiasOff + ((kExt && kHalves == 1) ? 2 * kBiasBufBytes : 0);
+  static constexpr int kBarOff = kBiasOff + (kExt ? 2 * kBiasBufBytes : 0);
   // barriers: q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full[2], bias_full[2], bias_empty[2]
   static constexpr int kNumBars = 1 + 4 * kStages + 6 + 4;
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
-  // row statistics exchanged between the kHalves threads of a row: [parity 2 x kind 2][tile 2][half 2][128 rows] fp32
-  static constexpr int kXchgOff = kTmemSlotOff + 16;
-  static constexpr int kBytes = kXchgOff + (kHalves == 2 ? 4 * 2 * 2 * kBM * 4 : 0);
+  static constexpr int kBytes = kTmemSlotOff + 16;
   static_assert(8 * kStageWarpBytes <= 2 * kBiasBufBytes, "the two bias layouts share one region");
   static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-byte alignment
   static_assert(kDynBytes <= 227 * 1024, "forward shared memory exceeds the 227 KB a CTA can have");
@@ -166,7 +107,6 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   [[maybe_unused]] uint64_t* bias_empty = bias_full + 2;
   [[maybe_unused]] uint8_t* sBias = smem + L::kBiasOff;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
-  float* xchg = reinterpret_cast<float*>(smem + L::kXchgOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -320,19 +260,15 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (i < nblk[t]) {
             mbar_wait(&p_full[t], i & 1);
             tcgen05_fence_after();
-            FA2_STAMP(2, i, t * 4 + 0);
             issue_pv(t, sv, i > 0);
-            FA2_STAMP(2, i, t * 4 + 1);
             if (i + 1 < nblk[t]) {
               if (!next_k_ready) {
                 mbar_wait(&k_full[sn], phn);
                 tcgen05_fence_after();
                 next_k_ready = true;
               }
-              FA2_STAMP(2, i, t * 4 + 2);
               issue_qk(t, sn);
               umma_commit(&s_full[t]);
-              FA2_STAMP(2, i, t * 4 + 3);
             } else {
               umma_commit(&o_full[t]);
             }
@@ -346,22 +282,20 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   } else {
     // ===================================== softmax warpgroups ====================================
     reg_alloc<kRegsSmx>();
-    const int t = warp / (4 * kHalves);       // Q tile
-    const int half = (warp >> 2) % kHalves;   // which kCols key columns of every block
+    const int t = warp >> 2;                  // Q tile
     const int r = threadIdx.x & 127;          // row inside the tile == TMEM lane
     const int tile_row0 = row0 + t * kBM;
     const int row = tile_row0 + r;
     const int nblk = t == 0 ? nblk0 : nblk1;
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + t * kBN + half * kCols;  // this thread's scores; P goes over their head
-    constexpr int kOCols = D / kHalves;                                 // columns of O this thread rescales / stores
-    const uint32_t tO = tmem_base + lane_sel + 256 + t * D + half * kOCols;
+    const uint32_t tS = tmem_base + lane_sel + t * kBN;  // this thread's scores; P goes over their head
+    constexpr int kOCols = D;                            // columns of O this thread rescales / stores
+    const uint32_t tO = tmem_base + lane_sel + 256 + t * D;
     const float c = p.scale_log2;
     const int shift = Sk - Sq;
-    auto xchg_slot = [&](int par, int h, int kind = 0) { return xchg + (((par * 2 + kind) * 2 + t) * 2 + h) * kBM + r; };
 
     float m_ref = -INFINITY;
-    float l = 0.f;  // kHalves == 2: the sum over this thread's columns only
+    float l = 0.f;
     // linear index of this row's first score in a [B, Hq, Sq, Sk] tensor, modulo 2^32: the dropout counter
     // (src/forward/kernel.py:147-149)
     const uint32_t drop_row_off =
@@ -383,7 +317,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       for (int j = 0; j < 2; ++j)
         tma_load_4d(my_bias + j * L::kBiasSubBytes, &tmap_bias, &bias_full[t], blk * kBN + j * 64, tile_row0, bias_h, bias_b);
     };
-    if constexpr ((kExt & 1) && kHalves == 1) {
+    if constexpr ((kExt & 1) != 0) {
       if (kBiasTma && nblk > 0 && r == 0) {
         tma_prefetch_desc(&tmap_bias);
         bias_issue(0);
@@ -391,7 +325,6 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
 
     for (int i = 0; i < nblk; ++i) {
-      if (r == 0 && half == 0) FA2_STAMP(t, i, 0);
       // ---- kExt: additive bias (src/forward/compute_row_blocks.py:48-54, 68-69) ----
       // It joins the raw scores as bias / softmax_scale, so that the common factor c = softmax_scale * log2(e) applies
       // to both; hidden entries are set to -inf afterwards. A thread owns a score row, so reading its 128 bias values
@@ -500,7 +433,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           bias_issue(i + 1);
         }
       };
-      if constexpr ((kExt & 1) && kHalves == 1) {
+      if constexpr ((kExt & 1) != 0) {
         if (p.bias.ptr != nullptr) {
           if constexpr (kBiasTma) bias_take();
           else if (p.bias.is_fp32) bias_fetch(std::integral_constant<int, 4>{}, 0);
@@ -517,7 +450,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           uint32_t bits = 0xffffffffu;
           if (p.dropout_p > 0.f) {
             bits = 0u;
-            const uint32_t off = drop_row_off + static_cast<uint32_t>(i * kBN + half * kCols + wd * 32);
+            const uint32_t off = drop_row_off + static_cast<uint32_t>(i * kBN + wd * 32);
 #pragma unroll 2
             for (int b = 0; b < 32; ++b)
               bits |= static_cast<uint32_t>(dropout_keep(p.seed_lo, p.seed_hi, off + b, p.dropout_p)) << b;
@@ -528,23 +461,18 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       (void)keep_bits;
       mbar_wait(&s_full[t], i & 1);
       tcgen05_fence_after();
-      if (r == 0 && half == 0) FA2_STAMP(t, i, 1);
       if constexpr ((kExt & 1) != 0) {
         if (p.bias.ptr != nullptr) {
-          if constexpr (kHalves == 1) {
-            if constexpr (kBiasTma) {
-              // added to the score registers below, without the round trip through tensor memory
-            } else if (p.bias.is_fp32) {  // 64 columns per pass: the second fetch is exposed (fp32 biases are the rare case)
-              bias_apply(std::integral_constant<int, 4>{}, 0);
-              bias_fetch(std::integral_constant<int, 4>{}, 1);
-              bias_apply(std::integral_constant<int, 4>{}, 1);
-            } else {
-              bias_apply(std::integral_constant<int, 2>{}, 0);
-            }
-            tmem_wait_st();
+          if constexpr (kBiasTma) {
+            // added to the score registers below, without the round trip through tensor memory
+          } else if (p.bias.is_fp32) {  // 64 columns per pass: the second fetch is exposed (fp32 biases are the rare case)
+            bias_apply(std::integral_constant<int, 4>{}, 0);
+            bias_fetch(std::integral_constant<int, 4>{}, 1);
+            bias_apply(std::integral_constant<int, 4>{}, 1);
           } else {
-            __trap();  // the staged bias path assumes one softmax thread per row (FA2_FWD_HALVES = 1, the default)
+            bias_apply(std::integral_constant<int, 2>{}, 0);
           }
+          tmem_wait_st();
         }
       }
 
@@ -558,7 +486,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int j = 0; j < kCols; ++j) s[j] = __uint_as_float(su[j / 32][j % 32]);
       };
       bool scores_loaded = false;
-      if constexpr ((kExt & 1) && kHalves == 1) {
+      if constexpr ((kExt & 1) != 0) {
         if constexpr (kBiasTma) {  // 64 scores at a time, so that at most 32 bias registers are live next to all 128 scores
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -582,9 +510,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
       }
       if (!scores_loaded) load_scores();
-      if (r == 0 && half == 0) FA2_STAMP(t, i, 2);
 
-      const int col0 = i * kBN + half * kCols;
+      const int col0 = i * kBN;
       const int block_last = i * kBN + kBN - 1;
       const bool need_mask = (block_last >= Sk) || (p.causal && block_last > tile_row0 + shift);
       if (need_mask) {
@@ -594,56 +521,6 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
 
       uint32_t pk[kCols / 2];
-      // Speculative fast path (every block but the first and the masked ones): exponentiate against the current
-      // reference maximum right away and find the block maximum on the side - the FMNMX run on the ALU pipe in the
-      // shadow of the MUFU. Only if some row of this warp turns out to exceed the reference by more than the rescale
-      // threshold is the block redone the slow way (scores reloaded from tensor memory - P has not been stored yet -
-      // maximum first, rescale O, exponentiate). Results are identical to always taking the slow path; the maximum
-      // pass leaves the softmax -> PV -> QK chain.
-      bool done = false;
-      if (FA2_FWD_SPEC && !(kExt & 1) && i > 0 && !need_mask) {
-        const float neg_m = -m_ref;  // m_ref == -inf (row without any visible key so far): x = +inf forces the slow path
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        float xm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int j = 0; j < kCols; j += 2) {
-          const float x0 = fmaf(s[j], c, neg_m), x1 = fmaf(s[j + 1], c, neg_m);
-          xm[(j / 2) % 4] = fmaxf(xm[(j / 2) % 4], fmaxf(x0, x1));
-          float p0, p1;
-          if (FA2_FWD_EMUL_NUM > 0 && ((j / 2) % FA2_FWD_EMUL_DEN) < FA2_FWD_EMUL_NUM) {
-            p0 = ex2_emul(x0);
-            p1 = ex2_emul(x1);
-          } else {
-            p0 = ex2_approx(x0);
-            p1 = ex2_approx(x1);
-          }
-          ls[j % 4] += p0;
-          ls[j % 4 + 1] += p1;
-          pk[j / 2] = pack2<kBf16>(p0, p1);
-        }
-        float xmax = fmaxf(fmaxf(xm[0], xm[1]), fmaxf(xm[2], xm[3]));
-        if constexpr (kHalves == 2) {
-          *xchg_slot(i & 1, half, 1) = xmax;
-          named_bar_sync(1 + t, kTileSmxThreads);
-          xmax = fmaxf(xmax, *xchg_slot(i & 1, half ^ 1, 1));
-        }
-        const bool redo = !(xmax <= kRescaleThreshold);
-        if (!__any_sync(0xffffffffu, redo)) {
-          l += (ls[0] + ls[2]) + (ls[1] + ls[3]);
-          done = true;
-        } else {
-          load_scores();
-        }
-      }
-      if (!done) {
-#if FA2_FWD_ABLATE >= 3
-      {
-#pragma unroll
-        for (int j = 0; j < kCols; j += 2) pk[j / 2] = pack2<kBf16>(s[j], s[j + 1]);
-        l = 1.f; m_ref = 0.f; done = true;
-      }
-      if (!done) {
-#endif
       float mx[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[j], s[j + 8]);
@@ -652,17 +529,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
         for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], fmaxf(s[j + e], s[j + e + 8]));
       }
-      float mb = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
-#if FA2_FWD_ABLATE == 2
-      mb = s[0] * c;
-#endif
-      if constexpr (kHalves == 2) {
-        // the two threads of a row must use the same reference maximum: swap block maxima (double buffered by parity:
-        // a slot is rewritten two blocks later, after the barrier of the block in between)
-        *xchg_slot(i & 1, half) = mb;
-        named_bar_sync(1 + t, kTileSmxThreads);
-        mb = fmaxf(mb, *xchg_slot(i & 1, half ^ 1));
-      }
+      const float mb = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * c;
 
       // lazy rescale: only move the reference max when the block max exceeds it by > 2^8
       const bool need = mb > m_ref + kRescaleThreshold;
@@ -685,86 +552,33 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       l *= alpha;
 
-      if (r == 0 && half == 0) FA2_STAMP(t, i, 3);
+      // every exponential on the MUFU: a bias may hold -inf (used as a mask), which must give exactly 0
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      auto exp_block = [&](auto emulate) {
 #pragma unroll
-        for (int j = 0; j < kCols; j += 2) {
-          float pr[2];
-#if FA2_FWD_EMUL_PACKED
-          // whole pairs on the FMA pipes with the f32x2 flavour (half the issue slots of the scalar one)
-          if (decltype(emulate)::value && ((j / 2) % FA2_FWD_EMUL_DEN) < FA2_FWD_EMUL_NUM) {
-            const float2 x2 = ffma2(make_float2(s[j], s[j + 1]), make_float2(c, c), make_float2(neg_m, neg_m));
-            const float2 p2 = ex2_emul2(x2);
-            pr[0] = p2.x;
-            pr[1] = p2.y;
-          } else {
-#if FA2_FWD_ABLATE >= 1
-            pr[0] = fmaf(s[j], c, neg_m);
-            pr[1] = fmaf(s[j + 1], c, neg_m);
-#elif FA2_FWD_EX2_F16
-            {
-              uint32_t xh, ph;
-              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(fmaf(s[j + 1], c, neg_m)), "f"(fmaf(s[j], c, neg_m)));
-              asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(xh));
-              const float2 pf2 = __half22float2(*reinterpret_cast<const __half2*>(&ph));
-              pr[0] = pf2.x;
-              pr[1] = pf2.y;
-            }
-#else
-            pr[0] = ex2_approx(fmaf(s[j], c, neg_m));
-            pr[1] = ex2_approx(fmaf(s[j + 1], c, neg_m));
-#endif
-          }
-          ls[j % 4] += pr[0];
-          ls[j % 4 + 1] += pr[1];
-          if constexpr ((kExt & 2) != 0) {
-            // dropout hits P after its row sum was taken (src/forward/compute_row_blocks.py:73-79)
-            pr[0] = ((keep_bits[j / 32] >> (j % 32)) & 1u) ? pr[0] : 0.f;
-            pr[1] = ((keep_bits[(j + 1) / 32] >> ((j + 1) % 32)) & 1u) ? pr[1] : 0.f;
-          }
-#else
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float x = fmaf(s[j + e], c, neg_m);
-            if (decltype(emulate)::value && ((j + e) % FA2_FWD_EMUL_DEN) < FA2_FWD_EMUL_NUM) {
-              pr[e] = ex2_emul(x);
-            } else {
-              pr[e] = ex2_approx(x);
-            }
-            ls[(j + e) % 4] += pr[e];
-          }
-#endif
-          pk[j / 2] = pack2<kBf16>(pr[0], pr[1]);
+      for (int j = 0; j < kCols; j += 2) {
+        float pr[2];
+        pr[0] = ex2_approx(fmaf(s[j], c, neg_m));
+        pr[1] = ex2_approx(fmaf(s[j + 1], c, neg_m));
+        ls[j % 4] += pr[0];
+        ls[j % 4 + 1] += pr[1];
+        if constexpr ((kExt & 2) != 0) {
+          // dropout hits P after its row sum was taken (src/forward/compute_row_blocks.py:73-79)
+          pr[0] = ((keep_bits[j / 32] >> (j % 32)) & 1u) ? pr[0] : 0.f;
+          pr[1] = ((keep_bits[(j + 1) / 32] >> ((j + 1) % 32)) & 1u) ? pr[1] : 0.f;
         }
-      };
-      // masked blocks keep every exponential on the MUFU (exact 0 for -inf scores); everywhere else a fixed share
-      // is evaluated on the FMA pipes
-      if (need_mask) exp_block(std::false_type{}); else exp_block(std::true_type{});
+        pk[j / 2] = pack2<kBf16>(pr[0], pr[1]);
+      }
       l += (ls[0] + ls[2]) + (ls[1] + ls[3]);
-      }
-#if FA2_FWD_ABLATE >= 3
-      }
-#endif
-      if (r == 0 && half == 0) FA2_STAMP(t, i, 4);
 #pragma unroll
       for (int cidx = 0; cidx < kCols / 64; ++cidx) tmem_st_32x32b_x32(tS + cidx * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[cidx * 32]));
       tmem_wait_st();
       tcgen05_fence_before();
       mbar_arrive(&p_full[t]);
-      if (r == 0 && half == 0) FA2_STAMP(t, i, 5);
     }
 
     // ------------------------------ epilogue: O / l -> smem -> TMA store ---------------------------
     if (tile_row0 < Sq) {
-      if constexpr (kHalves == 2) {
-        // full row sum = the two partial sums (both relative to the same m_ref); slots of parity nblk & 1 are free:
-        // the last block used parity (nblk - 1) & 1 and every thread has passed that block's barrier
-        *xchg_slot(nblk & 1, half) = l;
-        named_bar_sync(1 + t, kTileSmxThreads);
-        l += *xchg_slot(nblk & 1, half ^ 1);
-      }
       float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
       if constexpr ((kExt & 2) != 0) {
         if (p.dropout_p > 0.f) inv_l *= p.inv_keep;  // src/forward/kernel.py:256-257
@@ -788,7 +602,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = 0u;
         }
-        const int col = half * kOCols + cidx * 32;  // first head-dim column of this chunk
+        const int col = cidx * 32;  // first head-dim column of this chunk
         uint8_t* sub = sO + (col / 64) * kSubBytes;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -803,7 +617,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + t, kTileSmxThreads);
-      if (r == 0 && half == 0) {
+      if (r == 0) {
         if (p.seqlens != nullptr) tmap_acquire(mo);
         for (int j = 0; j < kSub; ++j) tma_store_4d(mo, sO + j * kSubBytes, j * 64, tile_row0, head, bc);
         bulk_commit_group();
@@ -811,7 +625,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       // LSE (log2 domain), padded rows get 0
       float* lse_row = p.lse + (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride;
-      if (half == 0 && row < p.lse_stride) {
+      if (row < p.lse_stride) {
         float lse = 0.f;
         if (row < Sq) lse = (l > 0.f) ? m_ref + lg2_approx(l) : -INFINITY;
         lse_row[row] = lse;
@@ -833,35 +647,22 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 template <int D, bool kBf16, int kExt>
 static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                 const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
-  auto kernel = fa2_fwd_kernel<D, kBf16, kExt>;
   constexpr int smem = FwdSmem<D, (kExt & 1) != 0, (kExt & 4) != 0>::kDynBytes;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<fa2_fwd_kernel<D, kBf16, kExt>>(smem); e != cudaSuccess) return e;
   dim3 grid(p.n_pairs, p.Hq, p.B);
   const CUtensorMap& tbias = (kExt & 4) ? *p.bias_map : tq;  // placeholder when no bias goes through TMA
-  kernel<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, tbias, p);
+  fa2_fwd_kernel<D, kBf16, kExt><<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, tbias, p);
   return cudaGetLastError();
 }
 
-#ifdef FA2_TRACE
-cudaError_t fetch_fwd_trace(long long* host, size_t n) {
-  return cudaMemcpyFromSymbol(host, g_fwd_trace, n * sizeof(long long));
-}
-#endif
-
+// D: the kernel head dim (64, 128 or 256). The plain forward and every head dim above 128 go to fwd2_sm100.cu.
 cudaError_t launch_fwd(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const CUtensorMap& to, const FwdParams& p, cudaStream_t stream) {
-  const int ext = (p.bias.ptr != nullptr ? (p.bias_tma && p.bias_map && kHalves == 1 ? 5 : 1) : 0) | (p.dropout_p > 0.f ? 2 : 0);
+  const int ext = (p.bias.ptr != nullptr ? (p.bias_tma && p.bias_map ? 5 : 1) : 0) | (p.dropout_p > 0.f ? 2 : 0);
+  if (ext == 0 || D == 256) return launch_fwd2(D, bf16, tq, tk, tv, to, p, stream);
 #define FA2_FWD_CASE(d, b)                                                                       \
   if (D == d && bf16 == b) {                                                                     \
     switch (ext) {                                                                               \
-      case 0: return launch_fwd_t<d, b, 0>(tq, tk, tv, to, p, stream);                           \
       case 1: return launch_fwd_t<d, b, 1>(tq, tk, tv, to, p, stream);                           \
       case 2: return launch_fwd_t<d, b, 2>(tq, tk, tv, to, p, stream);                           \
       case 3: return launch_fwd_t<d, b, 3>(tq, tk, tv, to, p, stream);                           \

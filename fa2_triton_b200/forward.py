@@ -27,27 +27,52 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-SUPPORTED_HEAD_DIMS = (64, 128)  # the kernel instantiations
+SUPPORTED_HEAD_DIMS = (64, 128, 256)  # the kernel instantiations
+FUSED_HEAD_DIMS = (64, 128)            # ... of the fused (atomic / ticket-ordered) backward
 
 
 def runs_natively(head_dim: int) -> bool:
-    """Head dims that go to the kernels as they are: multiples of 8 up to 128. TMA zero-fills the columns between the
-    tensor's head dim and the kernel's (64 or 128) on load and clips them on store - no padded copies."""
+    """Head dims that go to the kernels as they are: multiples of 8 up to 256. TMA zero-fills the columns between the
+    tensor's head dim and the kernel's (64, 128 or 256) on load and clips them on store - no padded copies."""
     return 8 <= head_dim <= SUPPORTED_HEAD_DIMS[-1] and head_dim % 8 == 0
 
 
-def padded_head_dim(head_dim: int) -> int:
-    """Any other head dim up to 128 (odd ones like 59 or 111: TMA needs 16-byte strides) runs on zero-padded copies of
-    the next kernel head dim: zero columns add nothing to Q K^T and produce zero columns of O, dQ, dK, dV. The reference
-    pads to the next power of two inside its kernels the same way (src/forward/caller.py:77-78, PADDED_HEADS)."""
-    for d in SUPPORTED_HEAD_DIMS:
-        if head_dim <= d:
+def padded_head_dim(head_dim: int, dims=None) -> int:
+    """Any other head dim up to 256 (odd ones like 59, 111 or 207: TMA needs 16-byte strides) runs on zero-padded copies:
+    zero columns add nothing to Q K^T and produce zero columns of O, dQ, dK, dV. The reference pads to the next power of
+    two inside its kernels the same way (src/forward/caller.py:77-78, PADDED_HEADS). Without ``dims`` the copy is padded
+    to the next multiple of 8 (what TMA needs); with ``dims`` to the first of those head dims that holds it."""
+    if dims is None:
+        d = max(8, (head_dim + 7) // 8 * 8)
+        if d <= SUPPORTED_HEAD_DIMS[-1]:
             return d
+    else:
+        for d in dims:
+            if head_dim <= d:
+                return d
     raise NotImplementedError(f"head_dim {head_dim}: this build supports head dims up to {SUPPORTED_HEAD_DIMS[-1]}")
 
 
 def pad_last(x: Tensor, d: int) -> Tensor:
     return x if x.shape[-1] == d else torch.nn.functional.pad(x, (0, d - x.shape[-1]))
+
+
+def kernel_addressable(x: Tensor) -> Tensor:
+    """``x`` itself if TMA can address it, else a contiguous copy.
+
+    The reference's Triton kernels take any strides (pointer arithmetic, src/forward/caller.py:93-96). TMA wants a
+    contiguous last dimension, a 16-byte aligned base, every other stride a multiple of 8 elements - and no zero stride
+    over a dimension of extent > 1: an EXPANDED tensor (k / v expanded over heads, or the dO autograd produces for
+    ``out.sum()``) would make the rows alias. Such tensors are materialised here, like ``src/wrapper.py:41-43`` does for
+    a non-contiguous last dimension."""
+    if x.dim() != 4:
+        return x
+    ok = x.stride(-1) == 1 and x.data_ptr() % 16 == 0
+    for dim in range(3):
+        st = x.stride(dim)
+        if x.size(dim) > 1 and (st == 0 or st % 8 != 0):
+            ok = False
+    return x if ok else x.contiguous()
 
 
 def device_sequence_lengths(attention_mask: Tensor) -> Tensor:
@@ -121,6 +146,8 @@ def _flash_attn_forward(
     batch, seqlen_q, nheads_q, head_dim = q.shape
     _, seqlen_k, nheads_kv, _ = k.shape
     expected_kv_shape = (batch, seqlen_k, nheads_kv, head_dim)
+    if q.is_cuda and k.is_cuda and v.is_cuda and runs_natively(head_dim):
+        q, k, v = kernel_addressable(q), kernel_addressable(k), kernel_addressable(v)
     if attention_mask is not None:
         assert bias is None, "Attention mask is not supported along with attention bias. Just use bias instead."
         if dropout_p and dropout_p > 0:

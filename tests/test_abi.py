@@ -59,8 +59,12 @@ def test_argument_errors_need_no_gpu():
     ptr = (ctypes.addressof(buf) + 15) & ~15
     rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 44, s, s, s, s, 128, 0.1, 0, 17, None)
     assert rc == _lib.E_UNSUPPORTED_HEAD_DIM and b"head_dim 44" in lib.fa2_sm100_last_error()
-    rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 136, s, s, s, s, 128, 0.1, 0, 17, None)
+    rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 264, s, s, s, s, 128, 0.1, 0, 17, None)
     assert rc == _lib.E_UNSUPPORTED_HEAD_DIM
+    # an expanded tensor (zero stride over a dimension of extent > 1) is refused, not silently mis-addressed
+    z = (ctypes.c_int64 * 3)(128 * 8 * 64, 0, 8 * 64)
+    rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 64, z, s, s, s, 128, 0.1, 0, 17, None)
+    assert rc == _lib.E_BAD_SHAPE and b"expanded" in lib.fa2_sm100_last_error()
     rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 3, 128, 128, 64, s, s, s, s, 128, 0.1, 0, 17, None)
     assert rc == _lib.E_BAD_SHAPE
     rc = lib.fa2_sm100_fwd(ptr, ptr, ptr, ptr, ptr, 1, 8, 8, 128, 128, 64, s, s, s, s, 128, 0.1, 0, 32, None)

@@ -280,3 +280,27 @@ def test_new_paths_are_bit_repeatable(kind):
     for _ in range(9):
         for a, b in zip(first, once()):
             assert torch.equal(a, b)
+
+
+def test_backward_expanded_dout_and_kv():
+    """the dO autograd produces for out.sum() is an expanded tensor (every stride 0), and k / v may be
+    expanded over heads; both must give the gradients of their materialised copies (the reference's pointer arithmetic
+    takes such strides as they are)."""
+    q, k, v, _ = generate_test_data(2, 300, 300, 4, 1, 128, torch.bfloat16, DEV, 12)
+
+    def grads(expand):
+        qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+        ke, ve = (kk.expand(-1, -1, 4, -1), vv.expand(-1, -1, 4, -1)) if expand else (kk.repeat(1, 1, 4, 1), vv.repeat(1, 1, 4, 1))
+        out = fa2.flash_attn_func(qq, ke, ve, causal=True)
+        if expand:
+            out.sum().backward()  # dO = ones, expanded
+        else:
+            out.backward(torch.ones_like(out))
+        return qq.grad, kk.grad, vv.grad
+
+    a, b = grads(True), grads(False)
+    torch.cuda.synchronize()
+    for name, x, y in zip(("dQ", "dK", "dV"), a, b):
+        assert torch.equal(x, y), name
+    ref = er.fwd_bwd(q, k.repeat(1, 1, 4, 1), v.repeat(1, 1, 4, 1), torch.ones_like(q), causal=True)
+    assert_close_16("dQ", a[0], ref[1])

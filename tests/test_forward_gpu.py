@@ -45,6 +45,38 @@ def test_forward_matches_oracle(Sq, Sk, D, causal, dtype):
     run_case(2, Sq, Sk, 3, 3, D, causal, dtype)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [136, 192, 207, 256])
+@pytest.mark.parametrize("Sq,Sk", [(128, 128), (1, 239), (113, 203), (256, 512), (1023, 1024), (384, 129), (700, 64)])
+def test_forward_head_dims_above_128(Sq, Sk, D, causal, dtype):
+    """Head dims 129..256 (207 and 256 of the reference's grid, tests/test_fwd_bwd.py:16): the D = 256 instantiation of
+    fwd2_sm100.cu - one Q tile per CTA, K / V tiles of 64 keys; 207 through a copy padded to 208."""
+    run_case(2, Sq, Sk, 4, 2, D, causal, dtype, seed=D)
+
+
+def test_forward_long_rows_many_half_blocks():
+    """Enough 64-key half-blocks for every ring / barrier phase of fwd2_sm100.cu to wrap several times, ragged ends,
+    both tiles of a CTA with different block counts (causal) and Sq != Sk."""
+    run_case(1, 1500, 2100, 2, 1, 128, True, torch.bfloat16, seed=3)
+    run_case(1, 2100, 1500, 2, 2, 64, True, torch.bfloat16, seed=4)
+    run_case(1, 1090, 2050, 2, 2, 256, False, torch.bfloat16, seed=5)
+
+
+def test_forward_expanded_inputs_are_materialised():
+    """k / v expanded over heads (stride 0) must give the same result as their materialised copies."""
+    q, k, v, _ = generate_test_data(2, 300, 300, 4, 1, 64, torch.bfloat16, DEV, 11)
+    ke, ve = k.expand(-1, -1, 4, -1), v.expand(-1, -1, 4, -1)
+    assert ke.stride(2) == 0
+    o1 = fa2.flash_attn_func(q, ke, ve, causal=True)
+    o2 = fa2.flash_attn_func(q, ke.contiguous(), ve.contiguous(), causal=True)
+    assert torch.equal(o1, o2)
+    qb = q[:1].expand(2, -1, -1, -1)  # batch stride 0
+    o3 = fa2.flash_attn_func(qb, k, v, causal=False)
+    o4 = fa2.flash_attn_func(qb.contiguous(), k, v, causal=False)
+    assert torch.equal(o3, o4)
+
+
 @pytest.mark.parametrize("Hq,Hkv", [(8, 2), (4, 1), (9, 9)])
 def test_forward_gqa(Hq, Hkv):
     run_case(2, 300, 300, Hq, Hkv, 128, True, torch.bfloat16)

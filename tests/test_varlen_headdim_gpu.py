@@ -155,8 +155,8 @@ def test_native_head_dim_strided_views_and_no_stray_writes():
         assert_close_16(name, g, r)
 
 
-def test_head_dim_above_128_is_rejected():
-    q, k, v, _ = generate_test_data(1, 128, 128, 2, 2, 256, torch.bfloat16, DEV)
+def test_head_dim_above_256_is_rejected():
+    q, k, v, _ = generate_test_data(1, 128, 128, 2, 2, 264, torch.bfloat16, DEV)
     with pytest.raises(NotImplementedError):
         fa2.flash_attn_func(q, k, v)
 
