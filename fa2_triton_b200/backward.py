@@ -47,6 +47,8 @@ def _backward_varlen(dO, q, k, v, attention_mask, o, lse, causal, softmax_scale,
     spilled-dS path (or dK / dV alone when dq is None). Returns False - the caller then falls back to one call per
     sequence - when the dS workspace of the padded shape does not fit. dq / dk / dv arrive zero-filled."""
     batch, seqlen, nheads_q, head_dim = q.shape
+    if head_dim > 128:
+        return False  # the backward kernels for head dims 129..256 take one sequence per launch
     nheads_kv = k.shape[2]
     seqlen_rounded = math.ceil(seqlen / 128) * 128
     scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
@@ -184,6 +186,9 @@ def _flash_attn_backward(
         mode = (_lib.DQ_DET_SPILL if spill else _lib.DQ_DETERMINISTIC) if det else _lib.DQ_ATOMIC
     else:
         mode = int(det) if det in (0, 1, 2, 5) else int(bool(det))  # one of _lib.DQ_*
+    if head_dim > 128 and mode in (_lib.DQ_ATOMIC, _lib.DQ_FUSED_ORDERED, _lib.DQ_DETERMINISTIC):
+        # head dims 129..256 have one backward: deterministic, dQ in its own kernel, P / dS tiles spilled for dK / dV
+        mode, auto = _lib.DQ_DET_SPILL, False
     if not need_dq and not need_dkdv:
         return None, None, None
     if not need_dq:

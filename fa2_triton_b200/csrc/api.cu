@@ -352,6 +352,12 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq, int B, int Hq, int Sq,
 
 size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int causal, int deterministic) {
   if (B < 1 || Hq < 1 || Sq < 1 || D < 1) return 0;
+  if (D > 128) {
+    // head dims 129..256 (bwd256_sm100.cu), every supported mode: counter + the dS tiles + the P tiles
+    if (Sk < 1) return 0;
+    const long long tiles = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);
+    return 1024 + 2 * static_cast<size_t>(B) * Hq * static_cast<size_t>(tiles) * fa2::kDsTileBytes;
+  }
   if (deterministic == FA2_DQ_NONE || deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_ONLY)
     return 256;  // no accumulator, only the work-item counters of the persistent kernels' schedulers
   if (deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ) {
@@ -428,7 +434,77 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
   fa2::BiasView bias_view{};
   if (int e = make_bias_view(&bias_view, bias, bias_dtype, bias_strides, dtype)) return e;
   const int Dk = kernel_head_dim(D);
-  if (D > 128) return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: the backward is built for head dims up to 128", D);
+  if (D > 128) {
+    // Head dims 129..256 (bwd256_sm100.cu): one deterministic path - dQ with spilled P / dS tiles, then dK / dV from the
+    // tiles. `deterministic` 1 (recompute) and 5 (spill) both select it; 3 / 4 skip dQ / dK + dV.
+    if (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED || deterministic == FA2_DQ_SPILL_DKDV ||
+        deterministic == FA2_DQ_SPILL_DQ)
+      return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: the backward above head dim 128 has the deterministic modes 1, 3, 4, 5 only", D);
+    if (seqlens) return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: variable-length mode stops at head dim 128 in the backward", D);
+    const bool want_dq = deterministic != FA2_DQ_NONE, want_dkdv = deterministic != FA2_DQ_ONLY;
+    if (!lse || !delta) return fail(FA2_E_NULL_POINTER, "lse / delta: null pointer");
+    if (want_dq && !dq) return fail(FA2_E_NULL_POINTER, "dq: null pointer");
+    if (want_dkdv && (!dk || !dv)) return fail(FA2_E_NULL_POINTER, "dk / dv: null pointer");
+    if (lse_row_stride != round_up(Sq, 128)) return fail(FA2_E_BAD_SHAPE, "lse_row_stride must be ceil(Sq/128)*128");
+    if (!(softmax_scale > 0.f)) return fail(FA2_E_BAD_SHAPE, "softmax_scale must be positive");
+    if (want_dq) {
+      if (dq_dtype != dtype && dq_dtype != FA2_DTYPE_FP32)
+        return fail(FA2_E_UNSUPPORTED_DTYPE, "dq_dtype %d: must be the input dtype (%d) or 32 (fp32)", dq_dtype, dtype);
+      if (reinterpret_cast<uintptr_t>(dq) % 16) return fail(FA2_E_BAD_ALIGNMENT, "dq: base not 16-byte aligned");
+      for (int i = 0; i < 3; ++i)
+        if (dq_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "dq: strides must be multiples of 8 elements");
+    }
+    if (want_dkdv) {
+      if (reinterpret_cast<uintptr_t>(dk) % 16 || reinterpret_cast<uintptr_t>(dv) % 16)
+        return fail(FA2_E_BAD_ALIGNMENT, "dk / dv: base not 16-byte aligned");
+      for (int i = 0; i < 3; ++i)
+        if (dk_strides[i] % 8 || dv_strides[i] % 8) return fail(FA2_E_BAD_ALIGNMENT, "dk / dv: strides must be multiples of 8 elements");
+    }
+    const size_t need256 = fa2_sm100_bwd_workspace_bytes(B, Hq, Sq, Sk, D, causal, FA2_DQ_DET_SPILL);
+    if (!workspace) return fail(FA2_E_NULL_POINTER, "workspace: null pointer");
+    if (workspace_bytes < need256) return fail(FA2_E_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed", workspace_bytes, need256);
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FA2_E_BAD_ALIGNMENT, "workspace not 16-byte aligned");
+    CUtensorMap tq, tk, tv, tdo;
+    if (int e = make_tmap_bshd(&tq, q, dtype, B, Sq, Hq, D, q_strides, 128, "q")) return e;
+    if (int e = make_tmap_bshd(&tk, k, dtype, B, Sk, Hkv, D, k_strides, 64, "k")) return e;
+    if (int e = make_tmap_bshd(&tv, v, dtype, B, Sk, Hkv, D, v_strides, 64, "v")) return e;
+    if (int e = make_tmap_bshd(&tdo, dout, dtype, B, Sq, Hq, D, do_strides, 128, "dout")) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t ce = cudaMemsetAsync(workspace, 0, 128, st);  // scheduler counter (the kernel re-zeroes it; first use of the buffer)
+    if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd scheduler counter memset");
+    const long long tiles = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);
+    const size_t region = static_cast<size_t>(B) * Hq * static_cast<size_t>(tiles) * fa2::kDsTileBytes;
+    fa2::Bwd256Params b{};
+    b.lse = lse; b.delta = delta;
+    b.ds_spill = static_cast<char*>(workspace) + 1024;
+    b.p_spill = static_cast<char*>(workspace) + 1024 + region;
+    b.tiles_per_head = tiles;
+    b.sched = static_cast<int*>(workspace);
+    b.dq = want_dq ? dq : nullptr;
+    b.dk = dk; b.dv = dv;
+    for (int i = 0; i < 3; ++i) {
+      b.dq_strides[i] = want_dq ? dq_strides[i] : 0;
+      b.dk_strides[i] = want_dkdv ? dk_strides[i] : 0;
+      b.dv_strides[i] = want_dkdv ? dv_strides[i] : 0;
+    }
+    b.dq_is_16bit = dq_dtype == dtype ? 1 : 0;
+    b.B = B; b.Hq = Hq; b.Hkv = Hkv; b.Sq = Sq; b.Sk = Sk;
+    b.lse_stride = static_cast<int>(lse_row_stride);
+    b.softmax_scale = softmax_scale;
+    b.scale_log2 = softmax_scale * kLog2e;
+    b.causal = causal ? 1 : 0;
+    b.bias = bias_view;
+    b.d_actual = D;
+    b.d_steps = (D + 15) / 16;
+    b.d_cols = round_up(D, 16);
+    ce = fa2::launch_bwd_dq256(dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, b, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dQ (head dim 129..256) launch");
+    if (want_dkdv) {
+      ce = fa2::launch_bwd_acc256(dtype == FA2_DTYPE_BF16, tq, tdo, b, st);
+      if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd dK / dV (head dim 129..256) launch");
+    }
+    return 0;
+  }
   if (D != Dk && (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED))
     return fail(FA2_E_UNSUPPORTED_HEAD_DIM, "head_dim %d: the fused (atomic / ticket-ordered) backward needs 64 or 128; "
                                             "the deterministic modes take any multiple of 8 up to 128", D);

@@ -165,19 +165,20 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
 }
 
 cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream) {
-  const int dk = p.D <= 64 ? 64 : 128;  // instantiation; head dims in between are handled by the column guard
+  const int dk = p.D <= 64 ? 64 : p.D <= 128 ? 128 : 256;  // instantiation; head dims in between are handled by the column guard
   const int rows_per_block = 4 * (256 / (dk / 8));
   dim3 grid((p.lse_stride + rows_per_block - 1) / rows_per_block, p.Hq, p.B);
-  if (p.D < 8 || p.D > 128 || p.D % 8) return cudaErrorInvalidValue;
-  if (p.dq_accum != nullptr && p.D != dk) return cudaErrorInvalidValue;  // the accumulator layout needs D in {64, 128}
-  if (dk == 128) {
+  if (p.D < 8 || p.D > 256 || p.D % 8) return cudaErrorInvalidValue;
+  if (p.dq_accum != nullptr && (p.D != dk || dk == 256)) return cudaErrorInvalidValue;  // the accumulator layout needs D in {64, 128}
+  if (dk == 256) {
+    if (bf16) fa2_delta_kernel<256, true><<<grid, 256, 0, stream>>>(p);
+    else fa2_delta_kernel<256, false><<<grid, 256, 0, stream>>>(p);
+  } else if (dk == 128) {
     if (bf16) fa2_delta_kernel<128, true><<<grid, 256, 0, stream>>>(p);
     else fa2_delta_kernel<128, false><<<grid, 256, 0, stream>>>(p);
-  } else if (dk == 64) {
+  } else {
     if (bf16) fa2_delta_kernel<64, true><<<grid, 256, 0, stream>>>(p);
     else fa2_delta_kernel<64, false><<<grid, 256, 0, stream>>>(p);
-  } else {
-    return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }

@@ -232,6 +232,40 @@ struct DqSpillParams {
 };
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------
+// deterministic backward for head dims 129..256 (bwd256_sm100.cu)
+// ---------------------------------------------------------------------------------------------
+// Workspace: [scheduler counter, 1 KB][dS tiles][P tiles], each tile region [B][Hq][visible (m, n) pairs, m-major][32 KB]
+// like the spilled-dS path above, a tile being [16 groups of 8 keys][128 queries][16 B].
+struct Bwd256Params {
+  const float* lse;    // [B, Hq, lse_stride] log2 domain
+  const float* delta;  // [B, Hq, lse_stride]
+  void* ds_spill;
+  void* p_spill;
+  long long tiles_per_head;
+  int* sched;          // work-item counter of the dK / dV kernel, 0 on entry (the kernel re-zeroes it)
+  void* dq;            // [B, Sq, Hq, D] or nullptr (dQ not wanted)
+  int64_t dq_strides[3];  // batch, head, seq (elements)
+  int dq_is_16bit;
+  void* dk;            // [B, Sk, Hkv, D], input dtype
+  void* dv;
+  int64_t dk_strides[3];
+  int64_t dv_strides[3];
+  int B, Hq, Hkv, Sq, Sk;
+  int lse_stride;
+  float softmax_scale;
+  float scale_log2;
+  int causal;
+  BiasView bias;       // kernel variant kBias; ptr == nullptr otherwise
+  int d_actual;        // head dim of the tensors (multiple of 8, 129..256)
+  int d_steps, d_cols; // ceil(d / 16) k-steps of the products that reduce over the head dim; d rounded up to 16 = N of the others
+};
+// K / V maps with box rows 64, Q / dO maps with box rows 128
+cudaError_t launch_bwd_dq256(bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                             const CUtensorMap& tdo, const Bwd256Params& p, cudaStream_t stream);
+cudaError_t launch_bwd_acc256(bool bf16, const CUtensorMap& tq, const CUtensorMap& tdo, const Bwd256Params& p,
+                              cudaStream_t stream);
+
 struct DqConvertParams {
   const float* dq_accum;  // as written by the backward kernel
   void* dq;               // [B, Sq, Hq, D] with strides below

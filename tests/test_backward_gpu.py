@@ -304,3 +304,36 @@ def test_backward_expanded_dout_and_kv():
         assert torch.equal(x, y), name
     ref = er.fwd_bwd(q, k.repeat(1, 1, 4, 1), v.repeat(1, 1, 4, 1), torch.ones_like(q), causal=True)
     assert_close_16("dQ", a[0], ref[1])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [136, 192, 207, 256])
+@pytest.mark.parametrize("Sq,Sk", [(128, 128), (1, 239), (113, 203), (256, 512), (1023, 1024), (384, 129), (700, 64)])
+def test_backward_head_dims_above_128(Sq, Sk, D, causal, dtype):
+    """Head dims 129..256 (207 and 256 of the reference's grid, tests/test_fwd_bwd.py:16): bwd256_sm100.cu - dQ with
+    spilled P / dS tiles, dK / dV from the tiles; GQA 4:2; 207 through copies padded to 208."""
+    run_case(2, Sq, Sk, 4, 2, D, causal, dtype, seed=D)
+
+
+def test_backward_head_dim_256_modes_and_repeatability():
+    """fp32 dQ, skipped gradients and every `deterministic` request land on the one deterministic path; 5 runs bit-equal."""
+    q, k, v, do = generate_test_data(2, 520, 650, 6, 2, 256, torch.bfloat16, DEV, 21)
+    o, lse, scale, seed = fa2._flash_attn_forward(q, k, v, None, None, 0.0, True, None, None)
+    ref = er.fwd_bwd(q, k, v, do, causal=True)
+    base = None
+    for det in (True, False, 1, 2, 5, True, True):
+        dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, None, o, lse, 0.0, True, scale, seed, deterministic=det)
+        torch.cuda.synchronize()
+        assert dq.dtype == torch.float32
+        if base is None:
+            base = (dq, dk, dv)
+            for name, g, r in (("dQ", dq, ref[1]), ("dK", dk, ref[2]), ("dV", dv, ref[3])):
+                assert_close_16(name, g, r)
+        else:
+            for name, a, b in zip(("dQ", "dK", "dV"), base, (dq, dk, dv)):
+                assert torch.equal(a, b), f"{name} differs for deterministic={det}"
+    dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, None, o, lse, 0.0, True, scale, seed, need_dq=False)
+    assert dq is None and torch.equal(dk, base[1]) and torch.equal(dv, base[2])
+    dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, None, o, lse, 0.0, True, scale, seed, need_dkdv=False)
+    assert dk is None and dv is None and torch.equal(dq, base[0])

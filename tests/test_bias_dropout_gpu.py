@@ -206,3 +206,14 @@ def test_dropout_backward_is_not_implemented_like_the_reference():
     out = fa2.flash_attn_func(qq, k, v, dropout_p=0.1, dropout_seed=1)
     with pytest.raises(NotImplementedError):  # src/utils.py:87-88
         torch.autograd.grad(out, (qq,), do)
+
+
+@pytest.mark.parametrize("D", [207, 256])
+@pytest.mark.parametrize("causal", [False, True])
+def test_bias_head_dims_above_128(D, causal):
+    """The bias arm of the reference's grid at head dims 207 / 256 (tests/test_fwd_bwd.py:16-20): plain-load bias in
+    fwd2_sm100.cu and bwd256_sm100.cu; 16-bit and fp32 biases, broadcast and per-(batch, head), -inf as a mask."""
+    run_bias_case(2, 113, 203, 4, 2, D, causal, torch.bfloat16, (1, 1, 113, 203))
+    run_bias_case(2, 256, 512, 4, 2, D, causal, torch.float16, (2, 4, 256, 512))
+    run_bias_case(1, 200, 328, 2, 2, D, causal, torch.bfloat16, (1, 2, 200, 328), bias_dtype=torch.float32)
+    run_bias_case(1, 256, 384, 2, 2, D, False, torch.bfloat16, (1, 1, 256, 384), with_inf=True)

@@ -10,7 +10,7 @@ restated in units in the last place, see compare_results_fa below).
 
 Every pytest case below runs the reference's 10 (seqlen_q, seqlen_k) pairs - and, for forward + backward, its two head
 configurations - for one (dtype, causal, head_dim, mode) cell. Head dims 207 and 256 of the reference's backward grid
-are outside this build (NotImplementedError, tests/test_varlen_headdim_gpu.py)."""
+run in their own kernels (fwd2_sm100.cu with one Q tile per CTA, bwd256_sm100.cu)."""
 import warnings
 
 import pytest
@@ -93,7 +93,7 @@ def core(B, Hq, Hkv, Sq, Sk, D, causal, dropout_p, use_attention, use_bias, dtyp
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("causal", [False, True])
-@pytest.mark.parametrize("head_dim", [32, 40, 64, 111, 128])
+@pytest.mark.parametrize("head_dim", [32, 40, 64, 111, 128, 207, 256])
 @pytest.mark.parametrize("swap_seqlens, use_attention, use_bias", MODES_FWD_BWD)
 def test_fwd_bwd_grid(swap_seqlens, use_attention, use_bias, head_dim, causal, dtype):
     for nheads_q, nheads_kv in [(8, 2), (9, 9)]:
