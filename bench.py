@@ -9,7 +9,11 @@ dO ~ N(0, 1): the recipe of the reference's tests/utils.py:21-25). Default workl
 (weak scaling: the global batch is 4*N, sharded by batch with no collective on the data path).
 
 Rank 0 prints ONE JSON line: metric/value (device-timed, inputs resident in HBM), e2e (host buffers in, host
-buffers out, through fa2_triton_b200.host_api), roofline of the dominant kernel, cpu_baseline, clocks.
+buffers out, through fa2_triton_b200.host_api), roofline of the dominant kernel (per-kernel times taken interleaved in step
+order), a `sustained` block (the same step loop for >= 2 s, own clock samples, against the sustained cuBLAS peak),
+cpu_baseline, clocks, `triton_baseline` (the reference's own Triton kernels on this GPU when baseline/_ref holds the
+reference tree) and, for N > 1, `sharded_matches_single` and a `strong_cfg5` record (BASELINE config 5 partitioned over
+the N GPUs).
 """
 from __future__ import annotations
 
@@ -54,10 +58,10 @@ def peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.power_w, self.reasons, self.max_mhz = [], [], set(), None
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -85,6 +89,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 try:
+                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
@@ -102,8 +110,12 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2], "sm_min_mhz": s[0], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(s)}
+        if self.power_w:
+            pw = sorted(self.power_w)
+            out["power_w_median"], out["power_w_max"] = pw[len(pw) // 2], pw[-1]
+        return out
 
 
 def make_inputs(B, H, S, D, device, seed, torch):
@@ -124,6 +136,9 @@ def cpu_baseline_run(torch, w, steps, warmup, budget_s=20.0):
     sample of the workload; the oracle's cost is exactly linear in B*H so the rate carries over."""
     from oracle import eager_reference as er
 
+    # torch.distributed.run exports OMP_NUM_THREADS=1: take every host core explicitly, so that the CPU arm is the same
+    # at every --gpus N (only rank 0 runs it; the other ranks exit or idle)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     threads = torch.get_num_threads()
     S, D, causal, bwd = w["S"], w["D"], w["causal"], w["bwd"]
     S_s = min(S, 4096)  # keep the S x S fp32 score tensors within a few hundred MB
@@ -153,7 +168,7 @@ def cpu_baseline_run(torch, w, steps, warmup, budget_s=20.0):
     return dict(value=flops / dt / 1e12, unit="TFLOP/s", cores=threads, kind="port",
                 sample=f"B=1,H={hs},S={S_s},D={D},causal={causal},{'fwd+bwd' if bwd else 'fwd'}; "
                        f"{steps} steps of {dt * 1e3:.0f} ms; eager PyTorch fp32 math on bf16 inputs; "
-                       f"os.cpu_count()={os.cpu_count()}"), dt
+                       f"torch.set_num_threads(os.cpu_count()={os.cpu_count()})"), dt
 
 
 def run_reference_arm(args):
@@ -190,6 +205,9 @@ def main():
     ap.add_argument("--atomic", action="store_true", help="dQ in arrival order (fast mode) instead of deterministic")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-triton", action="store_true", help="skip the reference's Triton kernels (baseline/_ref)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the config-5 strong-scaling record")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of the `sustained` block (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -264,10 +282,37 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
     value = flops_global / (ms_step * 1e-3) / 1e12
+    pk = peaks()
+
+    # ------------------------------- sustained: the same step loop for >= 2 s, own clock samples ------------------
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(math.ceil(args.sustain_s * 1e3 / ms_step)))
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        barrier()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            step()
+        s1.record()
+        torch.cuda.synchronize()
+        barrier()
+        sus_clocks = sampler.stop()
+        ts = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sus_ms = ts.item() / n_sus
+        sus_val = flops_global / (sus_ms * 1e-3) / 1e12
+        sustained = {"value": sus_val, "unit": "TFLOP/s", "steps": n_sus, "ms_per_step": sus_ms, "seconds": ts.item() * 1e-3,
+                     "frac_of_measured_sustained_peak": sus_val / world / pk["sustained"],
+                     "frac_of_measured_burst_peak": sus_val / world / pk["burst"], "clocks": sus_clocks}
 
     # -------------------------------- per-kernel timing (roofline of the dominant kernel) ------------------------
-    # Each kernel is launched alone through the C ABI with CUDA events on the launching stream on both sides.
-    pk = peaks()
+    # The step's kernels are launched through the C ABI in STEP ORDER (fwd, delta, dK/dV, dQ, fwd, ...), back to back, one
+    # CUDA-event pair per launch on the launching stream and a single synchronize at the end: every kernel is timed in the
+    # power / cache state it has inside a step, and the per-kernel times add up to the step (minus launch gaps).
     n_rep = min(args.steps, 20)
     o, lse, scale, _ = fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
     stream = torch.cuda.current_stream().cuda_stream
@@ -297,45 +342,37 @@ def main():
                                      B_local, H, H, S, S, D, s3(do), s3(q), s3(k), s3(v), s3(dq), s3(dk), s3(dv),
                                      S_pad, scale, int(causal), mode, 17, 17, stream), "bwd")
 
-    def time_call(fn, pre=None):
-        # back-to-back launches, one event pair per launch on the launching stream, a single synchronize at the end:
-        # the GPU never idles between launches (with a host sync after every launch the next kernel starts from a
-        # dropped clock state and times 20-30 % slower than inside a step)
-        evs = []
-        for i in range(n_rep + 2):
-            if pre is not None:
-                pre()
+    f_fwd = fa_flops(B_local, H, S, S, D, causal, False)
+    seq = [("fa2_fwd2_kernel", call_fwd, f_fwd, None)]
+    if bwd:
+        seq.append(("fa2_delta_kernel", call_delta, 0.0, None))
+        if args.atomic:
+            dom = "fa2_bwd_kernel<fused dQ> + fa2_dq_convert_kernel"
+            seq.append((dom, lambda: call_bwd(_lib.DQ_ATOMIC), 2.5 * f_fwd, None))
+        else:
+            # S, dP, dV, dK are the dK/dV kernel's products (it also spills dS); the dQ kernel's one product is dS K
+            dom = "fa2_bwd_dkdv_kernel<spill>"
+            seq.append((dom, lambda: call_bwd(_lib.DQ_SPILL_DKDV), 2.0 * f_fwd, None))
+            seq.append(("fa2_bwd_dq_spill_kernel", lambda: call_bwd(_lib.DQ_SPILL_DQ), 0.5 * f_fwd,
+                        float(ws_bytes - 1024 + 2 * q.numel() * 2)))
+    else:
+        dom = "fa2_fwd2_kernel"
+    events = {name: [] for name, _, _, _ in seq}
+    for i in range(n_rep + 2):
+        for name, fn, _, _ in seq:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
             b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs[2:]) / n_rep
-
-    f_fwd = fa_flops(B_local, H, S, S, D, causal, False)
-    kern = {"fa2_fwd_kernel": {"ms": time_call(call_fwd), "algorithmic_flop": f_fwd}}
-    if bwd:
-        kern["fa2_delta_kernel"] = {"ms": time_call(call_delta), "algorithmic_flop": 0.0}
-        if args.atomic:
-            # the fused launch needs a cleared accumulator each time: the delta kernel does that, outside the events
-            kern["fa2_bwd_kernel<fused dQ> + fa2_dq_convert_kernel"] = {
-                "ms": time_call(lambda: call_bwd(_lib.DQ_ATOMIC), pre=call_delta), "algorithmic_flop": 2.5 * f_fwd}
-            dom = "fa2_bwd_kernel<fused dQ> + fa2_dq_convert_kernel"
-        else:
-            call_delta()
-            # S, dP, dV, dK are the dK/dV kernel's products (it also spills dS); the dQ kernel's one product is dS K
-            kern["fa2_bwd_dkdv_kernel<spill>"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_SPILL_DKDV)), "algorithmic_flop": 2.0 * f_fwd}
-            kern["fa2_bwd_dq_spill_kernel"] = {"ms": time_call(lambda: call_bwd(_lib.DQ_SPILL_DQ)), "algorithmic_flop": 0.5 * f_fwd,
-                                               "bound": "hbm", "algorithmic_bytes": float(ws_bytes - 1024 + 2 * q.numel() * 2)}
-            dom = "fa2_bwd_dkdv_kernel<spill>"
-    else:
-        dom = "fa2_fwd_kernel"
-    for v_ in kern.values():
-        v_["tflops"] = v_["algorithmic_flop"] / (v_["ms"] * 1e-3) / 1e12 if v_["ms"] > 0 else 0.0
-        if "algorithmic_bytes" in v_:  # HBM-bound kernels: bytes each launch has to move / its duration
-            v_["gbs"] = v_["algorithmic_bytes"] / (v_["ms"] * 1e-3) / 1e9
-            v_["frac_of_hbm_peak"] = v_["gbs"] / pk["hbm"]
+            events[name].append((a, b))
+    torch.cuda.synchronize()
+    kern = {}
+    for name, _, flop, nbytes in seq:
+        ms = sum(a.elapsed_time(b) for a, b in events[name][2:]) / n_rep
+        kern[name] = {"ms": ms, "algorithmic_flop": flop, "tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+        if nbytes is not None:  # HBM-bound kernels: bytes each launch has to move / its duration
+            kern[name].update(bound="hbm", algorithmic_bytes=nbytes, gbs=nbytes / (ms * 1e-3) / 1e9,
+                              frac_of_hbm_peak=nbytes / (ms * 1e-3) / 1e9 / pk["hbm"])
     achieved = kern[dom]["tflops"]
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
@@ -344,12 +381,13 @@ def main():
             traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dom)
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["burst"], "unit": "TFLOP/s",
-                "frac": achieved / pk["burst"], "traffic": traffic,
-                "peak_source": pk["source"] + " cuBLAS bf16 burst (kernel timed alone)",
-                "frac_of_sustained": achieved / pk["sustained"], "frac_of_nominal_2250": achieved / 2250.0,
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["sustained"], "traffic": traffic,
+                "peak_source": pk["source"] + " cuBLAS bf16 SUSTAINED (the kernel is timed inside back-to-back steps)",
+                "frac_of_burst": achieved / pk["burst"], "frac_of_nominal_2250": achieved / 2250.0,
                 "algorithmic_flop_per_launch": kern[dom]["algorithmic_flop"], "kernel_ms": kern[dom]["ms"],
-                "kernels": kern}
+                "sum_of_kernels_ms": sum(v_["ms"] for v_ in kern.values()),
+                "timing": "interleaved in step order, one CUDA-event pair per launch", "kernels": kern}
 
     # ------------------------------------------------- e2e --------------------------------------------------------
     e2e = None
@@ -379,12 +417,50 @@ def main():
         e2e = {"value": flops_global / tt.item() / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": plan.h2d_bytes,
                "d2h_bytes_per_step": plan.d2h_bytes, "ms_per_step": tt.item() * 1e3, "steps": n_e2e,
                "api": "fa2_triton_b200.host_api.HostAttention (pinned host q,k,v,dO in; o,dq,dk,dv out; "
-                      f"{plan.chunks} (batch, head range) chunks over 3 streams, pitched copies, {plan.depth} steps in flight)"}
+                      f"{plan.chunks} (batch, head range) chunks over 3 streams, pitched copies, {plan.depth} steps in flight)",
+               "bound": "host<->device link: 512 MiB each way per step and GPU at config 3; the N GPUs of a box share the "
+                        "host's PCIe / memory bandwidth, so e2e does not scale with N (scripts/pcie_bw.py)"}
+        del plan, hp
+        torch.cuda.empty_cache()
+
+    # ---------------------- sharded == single: a foreign shard recomputed on rank 0 (verification only) -----------
+    sharded_ok = None
+    if world > 1 and bwd:
+        def checksums(ts):
+            # exact and order-independent: the 16-bit patterns summed as integers
+            return [int(t_.contiguous().view(torch.int16).to(torch.int64).sum().item()) for t_ in ts]
+
+        mine = checksums((step_out := run_step_outputs(fa2, torch, q, k, v, do, causal)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            other = 1  # rank 1's shard: weak scaling = its own batch elements (seed 1), strong = the next batch range
+            if w["scaling"] == "weak":
+                fq, fk, fv, fdo = make_inputs(B_local, H, S, D, dev, 0 + other, torch)
+            else:
+                ob = shard.merge_spans(shard.partition(B_global, H, world, other), H)[0]
+                fq, fk, fv, fdo = make_inputs(ob[1] - ob[0], H, S, D, dev, 0 + other, torch)
+            sharded_ok = checksums(run_step_outputs(fa2, torch, fq, fk, fv, fdo, causal)) == gathered[other]
+            del fq, fk, fv, fdo
+        del step_out
+
+    # ------------------------------- strong scaling of BASELINE config 5 over the N GPUs --------------------------
+    strong = None
+    if world > 1 and args.workload == "cfg3" and not args.no_strong:
+        del q, k, v, do, o, o2, dq, dk, dv, ws
+        torch.cuda.empty_cache()
+        strong = strong_cfg5(fa2, shard, torch, dist, dev, rank, world, barrier)
 
     # -------------------------------------------- CPU baseline (rank 0, N=1) --------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline_run(torch, w, steps=3, warmup=1, budget_s=20.0)
+
+    # ------------------------ the reference's own Triton kernels on this GPU (rank 0, needs baseline/_ref) ---------
+    triton_base = None
+    if rank == 0 and not args.no_triton and args.workload in ("cfg2", "cfg3"):
+        triton_base = triton_baseline_run(torch, w, dev, ms_step if world == 1 else None)
+    barrier()
 
     if rank == 0:
         line = {
@@ -399,12 +475,111 @@ def main():
             "frac_of_measured_burst_peak": value / world / pk["burst"],
             "frac_of_measured_sustained_peak": value / world / pk["sustained"],
             "frac_of_nominal_peak_2250": value / world / 2250.0,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * (4 if bwd else 1),  # fwd, delta, dK/dV (+dQ partials), dQ kernel or dQ convert
+            "sustained": sustained, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "triton_baseline": triton_base,
+            "gpu_launches": args.steps * (4 if bwd else 1),  # fwd, delta, dK/dV (+dS tiles), dQ kernel or dQ convert
         }
+        if world > 1:
+            line["sharded_matches_single"] = sharded_ok
+            line["strong_cfg5"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_step_outputs(fa2, torch, q, k, v, do, causal):
+    qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
+    out = fa2.flash_attn_func(qq, kk, vv, causal=causal)
+    grads = torch.autograd.grad(out, (qq, kk, vv), do)
+    torch.cuda.synchronize()
+    return (out.detach(),) + tuple(grads)
+
+
+def strong_cfg5(fa2, shard, torch, dist, dev, rank, world, barrier, steps=5):
+    """BASELINE config 5 (B=32, H=32, S=8192, D=128 causal fwd+bwd) partitioned over the `world` GPUs by
+    shard.partition (whole batch elements per rank): total work fixed, so value(N) / value(1) is the strong-scaling
+    speed-up. Timed like the main region: CUDA events, max over ranks."""
+    w = WORKLOADS["cfg5"]
+    B, H, S, D = w["B"], w["H"], w["S"], w["D"]
+    blocks = shard.merge_spans(shard.partition(B, H, world, rank), H)
+    if len(blocks) != 1 or blocks[0][2] != 0 or blocks[0][3] != H:
+        return {"unavailable": f"{world} ranks do not cut B={B} into whole batch elements"}
+    B_local = blocks[0][1] - blocks[0][0]
+    q, k, v, do = make_inputs(B_local, H, S, D, dev, 100 + rank, torch)
+
+    def step():
+        qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
+        out = fa2.flash_attn_func(qq, kk, vv, causal=True)
+        return torch.autograd.grad(out, (qq, kk, vv), do)
+
+    for _ in range(3):
+        step()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    flops = fa_flops(B, H, S, S, D, True, True)
+    return {"workload": workload_name("cfg5", w), "scaling": "strong", "n_gpus": world, "per_gpu_batch": B_local,
+            "steps": steps, "warmup": 3, "ms_per_step": ms, "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+            "note": "value at N=1 (whole problem on one GPU): python bench.py --workload cfg5"}
+
+
+def triton_baseline_run(torch, w, dev, ours_ms, steps=10):
+    """The reference's own Triton kernels (src/wrapper.py:89-100, UNMODIFIED, imported from the git-ignored copy of the
+    reference tree in baseline/_ref) on this GPU, same workload, same inputs recipe, CUDA events around back-to-back
+    steps after an autotuning first call + 3 warm-up steps. Returns None when baseline/_ref is absent."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "src" / "wrapper.py").exists():
+        return None
+    try:
+        import types
+
+        import triton.language as tl
+        if not hasattr(tl, "const_pointer_type"):  # SURVEY F2: the reference predates Triton 3.6
+            tl.const_pointer_type = tl.pointer_type
+        tmod = types.ModuleType("tests")          # SURVEY F4: another installed package is called `tests`
+        tmod.__path__ = [str(ref / "tests")]
+        sys.modules.setdefault("tests", tmod)
+        if str(ref) not in sys.path:
+            sys.path.insert(0, str(ref))
+        from src.wrapper import flash_attn_func as ref_func
+
+        B, H, S, D, causal, bwd = w["B"], w["H"], w["S"], w["D"], w["causal"], w["bwd"]
+        q, k, v, do = make_inputs(B, H, S, D, dev, 0, torch)
+
+        def step():
+            if bwd:
+                qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
+                out = ref_func(qq, kk, vv, causal=causal)
+                return torch.autograd.grad(out, (qq, kk, vv), do)
+            return ref_func(q, k, v, causal=causal)
+
+        for _ in range(4):  # the first call autotunes
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"value": fa_flops(B, H, S, S, D, causal, bwd) / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
+               "steps": steps, "what": "remi-or/fa2_triton src.wrapper.flash_attn_func (Triton 3.6, autotuned), unmodified, "
+                                       "one GPU, per-GPU workload"}
+        if ours_ms:
+            out["speedup_ours_over_triton"] = ms / ours_ms
+        return out
+    except Exception as e:  # a Triton that cannot compile / launch the reference is also a result
+        return {"unavailable": repr(e)[:500]}
 
 
 if __name__ == "__main__":

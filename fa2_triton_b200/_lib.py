@@ -64,7 +64,6 @@ SIGNATURES = {
     "fa2_sm100_dq_convert": (_c_int, [_c_void_p] * 2 + [_c_int] * 4 + [ctypes.POINTER(_c_int64)]
                              + [_c_float, _c_int, _c_void_p]),
     "fa2_sm100_copy2d_async": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_size_t, _c_size_t, _c_size_t, _c_int, _c_void_p]),
-    "fa2_sm100_debug_umma_probe": (_c_int, [_c_void_p] * 3 + [_c_int] * 5 + [_c_void_p]),
 }
 
 _lib = None

@@ -65,6 +65,26 @@ int make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype, int B, int S, i
       return fail(FA2_E_BAD_SHAPE, "%s: stride[%d] is 0 for a dimension of extent %d (expanded tensor): pass a "
                                    "materialised (contiguous) tensor", name, i, extent[i]);
   }
+  // A tensor map is a pure function of (address, dtype, extents, strides, box): a small per-thread cache saves the driver
+  // call for the tensors a training step passes again and again (11 maps per forward + backward).
+  struct Key {
+    const void* ptr; int dtype, B, S, H, D, box_rows; int64_t st[3];
+    bool operator==(const Key& o) const {
+      return ptr == o.ptr && dtype == o.dtype && B == o.B && S == o.S && H == o.H && D == o.D && box_rows == o.box_rows &&
+             st[0] == o.st[0] && st[1] == o.st[1] && st[2] == o.st[2];
+    }
+  };
+  struct Slot { Key key; CUtensorMap map; bool valid; };
+  constexpr int kSlots = 64;
+  thread_local Slot cache[kSlots] = {};
+  const Key key{ptr, dtype, B, S, H, D, box_rows, {strides[0], strides[1], strides[2]}};
+  uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
+  h = (h ^ (h >> 17)) * 0x9E3779B97F4A7C15ull + static_cast<uint64_t>(S) * 31 + static_cast<uint64_t>(box_rows) * 7 + static_cast<uint64_t>(strides[2]);
+  Slot& slot = cache[(h >> 20) % kSlots];
+  if (slot.valid && slot.key == key) {
+    *map = slot.map;
+    return 0;
+  }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(FA2_E_NO_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(H),
@@ -78,6 +98,9 @@ int make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype, int B, int S, i
   CUresult r = enc(map, dt, 4, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(static_cast<int>(r), "%s: cuTensorMapEncodeTiled failed with CUresult %d", name, static_cast<int>(r));
+  slot.key = key;
+  slot.map = *map;
+  slot.valid = true;
   return 0;
 }
 
@@ -97,8 +120,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // fa2_sm100_bwd_workspace_bytes_gqa in the header). Looks at the group size only, so that a (batch, kv-head) shard of a
 // call makes the same choice as the whole call and stays bit-identical to it.
 int kv_split_of(int Hq, int Hkv, int D, int deterministic) {
-  static const bool off = [] { const char* e = getenv("FA2_SM100_NO_KV_SPLIT"); return e && e[0] == '1'; }();
-  if (off || Hkv < 1 || Hq % Hkv) return 1;
+  if (Hkv < 1 || Hq % Hkv) return 1;
   if (deterministic == FA2_DQ_ATOMIC || deterministic == FA2_DQ_FUSED_ORDERED || deterministic == FA2_DQ_ONLY ||
       deterministic == FA2_DQ_SPILL_DQ)
     return 1;  // the fused kernel has no split variant; modes 4 and 7 do not run the dK / dV kernel
@@ -252,10 +274,9 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
   p.scale_log2 = softmax_scale * kLog2e;
   p.causal = causal ? 1 : 0;
   p.n_pairs = (Sq + 255) / 256;
-  // A/B switch for measurements: FA2_SM100_NO_DTRIM=1 issues the products of the zero-filled columns as well
-  static const bool no_dtrim = [] { const char* e = getenv("FA2_SM100_NO_DTRIM"); return e && e[0] == '1'; }();
-  p.d_steps = no_dtrim ? kernel_head_dim(D) / 16 : (D + 15) / 16;
-  p.d_cols = no_dtrim ? kernel_head_dim(D) : round_up(D, 16);
+  // head dims below the kernel's: the products of the zero-filled columns are not issued
+  p.d_steps = (D + 15) / 16;
+  p.d_cols = round_up(D, 16);
   if (int e = make_bias_view(&p.bias, bias, bias_dtype, bias_strides, dtype)) return e;
   p.bias_mul = 1.0f / softmax_scale;
   CUtensorMap tbias;
@@ -266,8 +287,7 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
     const int64_t bs[3] = {bias_strides[0], bias_strides[1], bias_strides[2]};
     const bool ok = reinterpret_cast<uintptr_t>(bias) % 16 == 0 && bs[0] % 8 == 0 && bs[1] % 8 == 0 && bs[2] % 8 == 0 &&
                     bs[2] > 0;
-    static const bool no_bias_tma = [] { const char* e = getenv("FA2_SM100_NO_BIAS_TMA"); return e && e[0] == '1'; }();
-    if (ok && !no_bias_tma && make_tmap_bshd(&tbias, bias, dtype, Bb, Sq, Hb, Sk, bs, 128, "bias") == 0) {
+    if (ok && make_tmap_bshd(&tbias, bias, dtype, Bb, Sq, Hb, Sk, bs, 128, "bias") == 0) {
       p.bias_tma = 1;
       p.bias_map = &tbias;
       p.bias_head_mul = Hb > 1 ? 1 : 0;
@@ -567,22 +587,19 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
   const bool spill = deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ;
   const long long tiles_per_head = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);
   void* spill_base = spill ? static_cast<char*>(workspace) + 1024 : nullptr;
-  if (!fused) {
-    // work-item counters of the persistent kernels (they re-zero them themselves; this covers the first use of the
-    // buffer): dQ kernel at byte 0, dK/dV kernel at byte 64
+  // Work-item counter of the persistent dQ kernel (byte 0 of the workspace; the kernel re-zeroes it when it is done, this
+  // covers the first use of a buffer). When the dK/dV kernel runs first, its CTA (0, 0, 0) clears the word - no memset
+  // node between the kernels, which would also break their programmatic dependent launch chain.
+  const bool dkdv_clears_counter = !fused && want_dkdv && !seqlens;
+  if (!fused && !dkdv_clears_counter) {
     ce = cudaMemsetAsync(workspace, 0, 128, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd scheduler counter memset");
   }
   int kv_split_used = 1;
   float* part_dk_used = nullptr;
   if (want_dkdv) {
-    // A/B switches: FA2_SM100_OLD_DKDV=1 the unfused instantiation of the fused kernel (P^T in tensor memory, dS^T in
-    // shared memory); FA2_SM100_DKDV_PERSISTENT=1 the persistent dK/dV kernel instead of one CTA per key block
-    // (measured 1.04 ms against 1.03: under the power cap hiding the per-CTA prologue buys nothing)
-    static const bool old_dkdv = [] { const char* e = getenv("FA2_SM100_OLD_DKDV"); return e && e[0] == '1'; }();
-    static const bool nonpersistent = [] { const char* e = getenv("FA2_SM100_DKDV_PERSISTENT"); return !(e && e[0] == '1'); }();
-    if (fused || (old_dkdv && !spill && !bias)) {
-      ce = fa2::launch_bwd(Dk, dtype == FA2_DTYPE_BF16, fused, tq, tk, tv, tdo, tdk, tdv, p, st);
+    if (fused) {
+      ce = fa2::launch_bwd(Dk, dtype == FA2_DTYPE_BF16, true, tq, tk, tv, tdo, tdk, tdv, p, st);
     } else {
       fa2::DkdvParams k{};
       k.lse = lse; k.delta = delta;
@@ -593,11 +610,7 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       k.softmax_scale = softmax_scale;
       k.scale_log2 = softmax_scale * kLog2e;
       k.causal = causal ? 1 : 0;
-      k.sched = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
-      k.dk = dk; k.dv = dv;
-      static const int dkdv_ctas = [] { const char* e = getenv("FA2_SM100_DKDV_CTAS"); return e ? atoi(e) : 0; }();
-      k.max_ctas = dkdv_ctas;  // experiments only (scripts/concurrent_probe.py): cap on the persistent grid
-      for (int i = 0; i < 3; ++i) { k.dk_strides[i] = dk_strides[i]; k.dv_strides[i] = dv_strides[i]; }
+      k.zero_word = dkdv_clears_counter ? static_cast<int*>(workspace) : nullptr;
       k.bias = bias_view;
       CUtensorMap tbias;
       if (bias && bias_dtype == dtype) {
@@ -607,8 +620,7 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
         const int64_t bs[3] = {bias_strides[0], bias_strides[1], bias_strides[2]};
         const bool ok = reinterpret_cast<uintptr_t>(bias) % 16 == 0 && bs[0] % 8 == 0 && bs[1] % 8 == 0 && bs[2] % 8 == 0 &&
                         bs[2] > 0;
-        static const bool no_bias_tma = [] { const char* e = getenv("FA2_SM100_NO_BIAS_TMA"); return e && e[0] == '1'; }();
-        if (ok && !no_bias_tma && make_tmap_bshd(&tbias, bias, dtype, Bb, Sq, Hb, Sk, bs, 128, "bias") == 0) {
+        if (ok && make_tmap_bshd(&tbias, bias, dtype, Bb, Sq, Hb, Sk, bs, 128, "bias") == 0) {
           k.bias_tma = 1;
           k.bias_map = &tbias;
           k.bias_head_mul = Hb > 1 ? 1 : 0;
@@ -619,7 +631,7 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       k.vmaps = vmaps;
       // large query-head groups: split over several CTAs when the caller's workspace has room for the fp32 partials
       // (sized with fa2_sm100_bwd_workspace_bytes_gqa); otherwise one CTA per (key block, kv head, batch) as before
-      int kv_split = (bias || seqlens || !nonpersistent) ? 1 : kv_split_of(Hq, Hkv, D, deterministic);
+      int kv_split = (bias || seqlens) ? 1 : kv_split_of(Hq, Hkv, D, deterministic);
       const size_t part_off = (need + 15) / 16 * 16;
       if (kv_split > 1 && workspace_bytes < part_off + kv_split_bytes(B, Hkv, Sk, D, kv_split)) kv_split = 1;
       k.kv_split = kv_split;
@@ -629,11 +641,9 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       }
       kv_split_used = kv_split;
       part_dk_used = k.part_dk;
-      static const bool no_dtrim = [] { const char* e = getenv("FA2_SM100_NO_DTRIM"); return e && e[0] == '1'; }();
-      k.d_steps = no_dtrim ? Dk / 16 : (D + 15) / 16;
-      k.d_cols = no_dtrim ? Dk : round_up(D, 16);
-      if (nonpersistent || bias || seqlens || D != Dk) ce = fa2::launch_bwd_dkdv(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
-      else ce = fa2::launch_bwd_dkdv_persistent(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, k, st);
+      k.d_steps = (D + 15) / 16;
+      k.d_cols = round_up(D, 16);
+      ce = fa2::launch_bwd_dkdv(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");
     if (kv_split_used > 1) {
@@ -664,8 +674,6 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
     d.B = B; d.Hq = Hq; d.Hkv = Hkv; d.Sq = Sq; d.Sk = Sk;
     d.softmax_scale = softmax_scale;
     d.causal = causal ? 1 : 0;
-    static const int dq_ctas = [] { const char* e = getenv("FA2_SM100_DQ_CTAS"); return e ? atoi(e) : 0; }();
-    d.max_ctas = dq_ctas;  // experiments only: cap on the persistent grid
     d.d_actual = D;
     d.seqlens = seqlens;
     d.vmaps = vmaps;
@@ -741,29 +749,5 @@ int fa2_sm100_debug_fetch_trace(int which, long long* host, size_t n) {
   }
 }
 #endif
-
-int fa2_sm100_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_mode, int b_mode, int dtype,
-                               void* stream) {
-  if (!is_16bit(dtype)) return fail(FA2_E_UNSUPPORTED_DTYPE, "dtype code %d", dtype);
-  if ((N != 64 && N != 128) || (K != 64 && K != 128)) return fail(FA2_E_BAD_SHAPE, "N and K must be 64 or 128");
-  if (a_mode < 0 || a_mode > 4 || b_mode < 0 || b_mode > 1) return fail(FA2_E_BAD_SHAPE, "bad operand mode");
-  if (!a || !b || !d) return fail(FA2_E_NULL_POINTER, "null pointer");
-  CUtensorMap ta, tb;
-  // A as [1, 128, 1, K]: strides (batch, head, seq) = (128*K, K, K)
-  const int64_t sa[3] = {128LL * K, K, K};
-  if (int e = make_tmap_bshd(&ta, a, dtype, 1, 128, 1, K, sa, 128, "probe a")) return e;
-  if (b_mode == 0) {
-    const int64_t sb[3] = {static_cast<int64_t>(N) * K, K, K};
-    if (int e = make_tmap_bshd(&tb, b, dtype, 1, N, 1, K, sb, N, "probe b")) return e;
-  } else {
-    const int64_t sb[3] = {static_cast<int64_t>(N) * K, N, N};
-    if (int e = make_tmap_bshd(&tb, b, dtype, 1, K, 1, N, sb, K, "probe b")) return e;
-  }
-  fa2::ProbeParams p{};
-  p.a = a; p.b = b; p.d = d; p.N = N; p.K = K; p.a_mode = a_mode; p.b_mode = b_mode;
-  cudaError_t ce = fa2::launch_probe(dtype == FA2_DTYPE_BF16, ta, tb, p, static_cast<cudaStream_t>(stream));
-  if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_debug_umma_probe launch");
-  return 0;
-}
 
 }  // extern "C"

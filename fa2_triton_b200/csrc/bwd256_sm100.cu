@@ -620,8 +620,7 @@ cudaError_t launch_bwd_dq256(bool bf16, const CUtensorMap& tq, const CUtensorMap
 template <bool kBf16>
 static cudaError_t launch_acc256_t(const CUtensorMap& tq, const CUtensorMap& tdo, const Bwd256Params& p, cudaStream_t stream) {
   if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_acc256_kernel<kBf16>>(Acc256Smem::kBytes); e != cudaSuccess) return e;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = current_sm_count();
   const int n_items = 2 * ((p.Sk + kBlk - 1) / kBlk) * p.Hkv * p.B;
   dim3 grid(n_items < sms ? n_items : sms);  // persistent: one CTA per SM
   fa2_bwd_acc256_kernel<kBf16><<<grid, kAccThreads, Acc256Smem::kBytes, stream>>>(tq, tdo, p);

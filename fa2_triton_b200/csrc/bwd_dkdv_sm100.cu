@@ -65,10 +65,7 @@ constexpr int kRegsIssue = kCmpWgs == 4 ? 64 : 88;
 constexpr int kQStages = 3;   // Q (+LSE) ring: Q(i) lives from S^T(i) to dK(i), and Q(i+1) is wanted right after dV(i)
 constexpr int kDoStages = 2;  // dO (+delta) ring
 // how many of every 4 pairs of exponentials are evaluated on the FMA pipes (ex2_emul2_neg) instead of the MUFU
-// persistent kernel: carry half of a thread's spill stores to the next iteration (costs ~10 registers)
-#ifndef FA2_DKDV_CARRY
-#define FA2_DKDV_CARRY 0
-#endif
+// (measured optimum; scripts/build_variants.sh rebuilds with another value for A/B runs)
 #ifndef FA2_DKDV_EMUL
 #define FA2_DKDV_EMUL 2
 #endif
@@ -229,6 +226,14 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tcgen05_fence_after();
   // whole-TMEM allocation => base 0; the literal keeps tcgen05 addresses warp-uniform for ptxas (see fwd_sm100.cu)
   if (*tmem_slot != 0u) __trap();
+  // PDL: the prologue above overlapped the tail of the previous kernel of the stream (the delta kernel); nothing below may
+  // run before it has completed
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    pdl_launch_dependents();
+    // the dQ kernel that follows on the stream draws its work items from this counter
+    if (p.zero_word != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *p.zero_word = 0;
+  }
 
   if (warp >= kMmaWarp) {
     reg_dealloc<kRegsIssue>();
@@ -631,501 +636,6 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-// =================================================================================================
-// Persistent variant: one CTA per SM walks (key block, kv head, batch) items handed out by an atomicAdd scheduler,
-// key blocks of one head consecutively (longest first), so that the CTAs running at any moment share the Q / dO of a
-// handful of heads in L2. The per-item prologue (K / V / Q / dO loads, ~6000 cycles before the first S^T) and epilogue
-// (accumulators -> registers -> global) of the one-CTA-per-item kernel above were ~20 % of a CTA's life: here the TMA
-// producer loads the next item's K / V as soon as the last S^T / dP^T of the current one are in the pipe, the MMA
-// thread issues S^T(0) / dP^T(0) of the next item while the compute warps still drain dK / dV, and dK / dV leave
-// straight from registers (no staging in the K / V tiles, which the next item already owns).
-// =================================================================================================
-namespace {
-constexpr int kSchedSlots = 4;
-enum PersistBar {
-  kKvEmpty = 18,    // the last S^T / dP^T of the item have read K / V
-  kAccEmpty = 19,   // dK / dV accumulators drained by the compute warps
-  kItemFull = 20,   // [4]
-  kItemEmpty = 24,  // [4]
-  kNumPersistBars = 28,
-};
-template <int D>
-struct DkdvPersistSmem {
-  using B = DkdvSmem<D>;
-  static constexpr int kBarOff = B::kBarOff;  // same tiles and rings
-  static constexpr int kSchedOff = kBarOff + kNumPersistBars * 8;
-  static constexpr int kTmemSlotOff = kSchedOff + kSchedSlots * 4;
-  static constexpr int kBytes = kTmemSlotOff + 16;
-  static_assert(kBytes <= 232448, "persistent dK/dV kernel smem budget exceeded");
-};
-struct KvItem {
-  int nblk, head_kv, batch;
-};
-__device__ __forceinline__ KvItem kv_item(int w, int n_kv_blocks, int Hkv) {
-  const int bh = w / n_kv_blocks;
-  KvItem it;
-  it.nblk = w - bh * n_kv_blocks;  // key block 0 (seen by the most query blocks under the causal mask) first
-  it.head_kv = bh % Hkv;
-  it.batch = bh / Hkv;
-  return it;
-}
-}  // namespace
-
-template <int D, bool kBf16, bool kSpill>
-__global__ void __launch_bounds__(kThreads, 1)
-fa2_bwd_dkdv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                               const DkdvParams p) {
-  using L = DkdvSmem<D>;
-  using LP = DkdvPersistSmem<D>;
-  constexpr int kSub = D / 64;
-  constexpr int kSubBytes = kBlk * 128;
-  constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
-  constexpr int kPairs = kCmpCols / 2;
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sK = smem + L::kKOff;
-  uint8_t* sV = smem + L::kVOff;
-  uint8_t* sQ = smem + L::kQOff;
-  uint8_t* sDO = smem + L::kDOOff;
-  float* sLse = reinterpret_cast<float*>(smem + L::kLseOff);
-  float* sDelta = reinterpret_cast<float*>(smem + L::kDeltaOff);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LP::kBarOff);
-  volatile int* sched = reinterpret_cast<volatile int*>(smem + LP::kSchedOff);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + LP::kTmemSlotOff);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_q_blocks = (p.Sq + kBlk - 1) / kBlk;
-  const int n_kv_blocks = (p.Sk + kBlk - 1) / kBlk;
-  const int n_items = n_kv_blocks * p.Hkv * p.B;
-  const int group = p.Hq / p.Hkv;
-  const int shift = p.Sk - p.Sq;
-  // iterations of an item: (head in group) x (query blocks from the first one that sees the key block)
-  auto m_start_of = [&](int nblk) { return p.causal ? max(0, (nblk * kBlk - shift) / kBlk) : 0; };
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-
-  if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    tma_prefetch_desc(&tmap_do);
-  }
-  if (warp == kMmaWarp) {
-    if (lane == 0) {
-      mbar_init(&bars[kKvFull], 1);
-      mbar_init(&bars[kKvEmpty], 1);
-      for (int s = 0; s < kQStages; ++s) {
-        mbar_init(&bars[kQFull + s], 1);
-        mbar_init(&bars[kQEmpty + s], 1);
-      }
-      for (int s = 0; s < kDoStages; ++s) {
-        mbar_init(&bars[kDoFull + s], 1);
-        mbar_init(&bars[kDoEmpty + s], 1);
-        mbar_init(&bars[kDeltaEmpty + s], kCmpThreads);
-      }
-      mbar_init(&bars[kSFull], 1);
-      mbar_init(&bars[kPFull], kCmpThreads);
-      mbar_init(&bars[kDpFull], 1);
-      mbar_init(&bars[kDsFull], kCmpThreads);
-      mbar_init(&bars[kDkvFull], 1);
-      mbar_init(&bars[kAccEmpty], kCmpThreads);
-      for (int i = 0; i < kSchedSlots; ++i) {
-        mbar_init(&bars[kItemFull + i], 1);
-        mbar_init(&bars[kItemEmpty + i], 1 + kCmpThreads);  // MMA thread + every compute thread
-      }
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc<512>(tmem_slot);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  if (*tmem_slot != 0u) __trap();  // whole-TMEM allocation => base 0 (keeps tcgen05 addresses warp-uniform)
-
-  // Counters shared by construction between the roles: t = items drawn so far (scheduler ring), tt = items with work
-  // (K / V barriers, accumulator hand-over), g = query-block iterations so far (Q / dO rings, per-iteration barriers).
-  if (warp >= kMmaWarp) {
-    reg_dealloc<kRegsIssue>();
-    if (warp == kTmaWarp) {
-      // ===================================== TMA producer + scheduler ================================
-      if (elect_one()) {
-        uint32_t tt = 0, g = 0;
-        for (uint32_t t = 0;; ++t) {
-          const uint32_t slot = t % kSchedSlots;
-          mbar_wait(&bars[kItemEmpty + slot], ((t / kSchedSlots) & 1) ^ 1);
-          const int w = atomicAdd(p.sched, 1);
-          // every CTA draws exactly one id past the end; the very last draw resets the counter for the next launch
-          if (w == n_items + static_cast<int>(gridDim.x) - 1) atomicExch(p.sched, 0);
-          sched[slot] = (w < n_items) ? w : -1;
-          mbar_arrive(&bars[kItemFull + slot]);
-          if (w >= n_items) break;
-          const KvItem item = kv_item(w, n_kv_blocks, p.Hkv);
-          const int m_start = m_start_of(item.nblk);
-          const int m_count = max(0, n_q_blocks - m_start);
-          const int T = m_count * group;
-          if (T == 0) continue;
-          const int kv0 = item.nblk * kBlk;
-          mbar_wait(&bars[kKvEmpty], (tt & 1) ^ 1);  // the previous item's last S^T / dP^T are done with K / V
-          mbar_arrive_expect_tx(&bars[kKvFull], 2 * L::kTileBytes);
-          for (int j = 0; j < kSub; ++j) {
-            tma_load_4d(sK + j * kSubBytes, &tmap_k, &bars[kKvFull], j * 64, kv0, item.head_kv, item.batch);
-            tma_load_4d(sV + j * kSubBytes, &tmap_v, &bars[kKvFull], j * 64, kv0, item.head_kv, item.batch);
-          }
-          for (int it = 0; it < T; ++it) {
-            const uint32_t gi = g + it;
-            const int qs = gi % kQStages, ds = gi % kDoStages;
-            const uint32_t qph = (gi / kQStages) & 1, dph = (gi / kDoStages) & 1;
-            const int head = item.head_kv * group + it / m_count;
-            const int m = m_start + it % m_count;
-            const int64_t row_off = (static_cast<int64_t>(item.batch) * p.Hq + head) * p.lse_stride + m * kBlk;
-            mbar_wait(&bars[kQEmpty + qs], qph ^ 1);
-            mbar_arrive_expect_tx(&bars[kQFull + qs], L::kTileBytes + kBlk * 4);
-            for (int j = 0; j < kSub; ++j)
-              tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, &tmap_q, &bars[kQFull + qs], j * 64, m * kBlk, head, item.batch);
-            bulk_load_1d(sLse + qs * kBlk, p.lse + row_off, kBlk * 4, &bars[kQFull + qs]);
-            mbar_wait(&bars[kDoEmpty + ds], dph ^ 1);
-            mbar_wait(&bars[kDeltaEmpty + ds], dph ^ 1);
-            mbar_arrive_expect_tx(&bars[kDoFull + ds], L::kTileBytes + kBlk * 4);
-            for (int j = 0; j < kSub; ++j)
-              tma_load_4d(sDO + ds * L::kTileBytes + j * kSubBytes, &tmap_do, &bars[kDoFull + ds], j * 64, m * kBlk, head, item.batch);
-            bulk_load_1d(sDelta + ds * kBlk, p.delta + row_off, kBlk * 4, &bars[kDoFull + ds]);
-          }
-          g += T;
-          ++tt;
-        }
-      }
-    } else if (warp == kMmaWarp) {
-      // ========================================== MMA issuer =========================================
-      if (elect_one()) {
-        constexpr uint32_t idesc_kk = make_idesc_f16(kBlk, kBlk, kBf16, false, false);  // S^T, dP^T
-        constexpr uint32_t idesc_tn = make_idesc_f16(kBlk, D, kBf16, false, true);      // dV, dK
-        const SmemDesc k_kmaj = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
-        const SmemDesc v_kmaj = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
-        const SmemDesc q_kmaj = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-        const SmemDesc do_kmaj = make_smem_desc_sw128(smem_u32(sDO), 16, 1024);
-        const SmemDesc q_mn = make_smem_desc_sw128(smem_u32(sQ), kSubBytes, 1024);
-        const SmemDesc do_mn = make_smem_desc_sw128(smem_u32(sDO), kSubBytes, 1024);
-        auto issue_kmajor = [&](uint32_t d_tmem, SmemDesc a, SmemDesc b) {
-#pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k / 4) * kSubBytes + (k % 4) * 32;
-            umma_ss(d_tmem, advance(a, off), advance(b, off), idesc_kk, k > 0 ? 1u : 0u);
-          }
-        };
-        auto issue_acc = [&](uint32_t d_tmem, uint32_t a_tmem, SmemDesc b_mn, bool accumulate) {
-#pragma unroll
-          for (int k = 0; k < kBlk / 16; ++k) {
-            constexpr int kStepsPerWg = kCmpCols / 16;
-            const uint32_t a_col = (k / kStepsPerWg) * kCmpCols + (k % kStepsPerWg) * 8;
-            umma_ts(d_tmem, a_tmem + a_col, advance(b_mn, k * 2048), idesc_tn, (accumulate || k > 0) ? 1u : 0u);
-          }
-        };
-
-        uint32_t tt = 0, g = 0;
-        for (uint32_t t = 0;; ++t) {
-          const uint32_t slot = t % kSchedSlots;
-          mbar_wait(&bars[kItemFull + slot], (t / kSchedSlots) & 1);
-          const int w = sched[slot];
-          mbar_arrive(&bars[kItemEmpty + slot]);
-          if (w < 0) break;
-          const KvItem item = kv_item(w, n_kv_blocks, p.Hkv);
-          const int T = max(0, n_q_blocks - m_start_of(item.nblk)) * group;
-          if (T == 0) continue;
-
-          mbar_wait(&bars[kKvFull], tt & 1);
-          mbar_wait(&bars[kQFull + g % kQStages], (g / kQStages) & 1);
-          tcgen05_fence_after();
-          issue_kmajor(kTmemS, k_kmaj, advance(q_kmaj, (g % kQStages) * L::kTileBytes));  // S^T(0) = K Q(0)^T
-          umma_commit(&bars[kSFull]);
-          mbar_wait(&bars[kDoFull + g % kDoStages], (g / kDoStages) & 1);
-          tcgen05_fence_after();
-          issue_kmajor(kTmemDP, v_kmaj, advance(do_kmaj, (g % kDoStages) * L::kTileBytes));  // dP^T(0) = V dO(0)^T
-          umma_commit(&bars[kDpFull]);
-          if (T == 1) umma_commit(&bars[kKvEmpty]);
-
-          for (int it = 0; it < T; ++it) {
-            const uint32_t gi = g + it;
-            const uint32_t par = gi & 1;
-            const int qs = gi % kQStages, qsn = (gi + 1) % kQStages;
-            const int ds = gi % kDoStages, dsn = (gi + 1) % kDoStages;
-            const uint32_t qphn = ((gi + 1) / kQStages) & 1, dphn = ((gi + 1) / kDoStages) & 1;
-            // dV (+)= P^T(it) dO(it)
-            mbar_wait(&bars[kPFull], par);
-            if (it == 0) mbar_wait(&bars[kAccEmpty], (tt & 1) ^ 1);  // the previous item's dK / dV have left TMEM
-            tcgen05_fence_after();
-            issue_acc(kTmemDV, kTmemS, advance(do_mn, ds * L::kTileBytes), it > 0);
-            umma_commit(&bars[kDoEmpty + ds]);
-            if (it + 1 < T) {
-              mbar_wait(&bars[kQFull + qsn], qphn);
-              tcgen05_fence_after();
-              issue_kmajor(kTmemS, k_kmaj, advance(q_kmaj, qsn * L::kTileBytes));
-              umma_commit(&bars[kSFull]);
-            }
-            // dK (+)= dS^T(it) Q(it)
-            mbar_wait(&bars[kDsFull], par);
-            tcgen05_fence_after();
-            issue_acc(kTmemDK, kTmemDP, advance(q_mn, qs * L::kTileBytes), it > 0);
-            umma_commit(&bars[kQEmpty + qs]);
-            if (it + 1 < T) {
-              mbar_wait(&bars[kDoFull + dsn], dphn);
-              tcgen05_fence_after();
-              issue_kmajor(kTmemDP, v_kmaj, advance(do_kmaj, dsn * L::kTileBytes));
-              umma_commit(&bars[kDpFull]);
-              if (it + 2 == T) umma_commit(&bars[kKvEmpty]);  // K / V have fed their last products
-            }
-          }
-          umma_commit(&bars[kDkvFull]);
-          g += T;
-          ++tt;
-        }
-      }
-    }
-  } else {
-    // ====================================== compute warpgroups =====================================
-    reg_alloc<kRegsCmp>();
-    const int wg = warp >> 2;
-    const int r = threadIdx.x & 127;  // key row inside the block == TMEM lane
-    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = lane_sel + kTmemS + wg * kCmpCols;
-    const uint32_t tDP = lane_sel + kTmemDP + wg * kCmpCols;
-    const float2 neg_c2 = make_float2(-p.scale_log2, -p.scale_log2);
-    constexpr int kPieces = kCmpCols / 8;
-    const int spill_thread_off = (wg * kPieces * kBlk + r) * 16;
-
-    uint32_t tt = 0, g = 0;
-    for (uint32_t t = 0;; ++t) {
-      const uint32_t slot = t % kSchedSlots;
-      mbar_wait(&bars[kItemFull + slot], (t / kSchedSlots) & 1);
-      const int w = sched[slot];
-      mbar_arrive(&bars[kItemEmpty + slot]);
-      if (w < 0) break;
-      const KvItem item = kv_item(w, n_kv_blocks, p.Hkv);
-      const int kv0 = item.nblk * kBlk;
-      const int kv = kv0 + r;
-      const int m_start = m_start_of(item.nblk);
-      const int m_count = max(0, n_q_blocks - m_start);
-      const int T = m_count * group;
-
-#if FA2_DKDV_CARRY
-      uint32_t carry[kPieces / 2 * 4];
-      uint8_t* carry_dst = nullptr;
-#endif
-      int prefix = 0;
-      for (int it = 0; it < T; ++it) {
-        const uint32_t gi = g + it;
-        const uint32_t par = gi & 1;
-        const int qs = gi % kQStages, ds = gi % kDoStages;
-        const uint32_t qph = (gi / kQStages) & 1, dph = (gi / kDoStages) & 1;
-        const int j_in_head = it % m_count;
-        const int m = m_start + j_in_head;
-        const int q0 = m * kBlk + wg * kCmpCols;
-        const float4* lse_s = reinterpret_cast<const float4*>(sLse + qs * kBlk + wg * kCmpCols);
-        const float4* delta_s = reinterpret_cast<const float4*>(sDelta + ds * kBlk + wg * kCmpCols);
-        const bool need_mask = (kv0 + kBlk > p.Sk) || (m * kBlk + kBlk > p.Sq) || (p.causal && (kv0 + kBlk - 1 > m * kBlk + shift));
-
-        // ---- P^T = exp2(S^T * c - LSE) ----
-        mbar_wait(&bars[kQFull + qs], qph);  // the LSE row travels with Q
-        mbar_wait(&bars[kSFull], par);
-        tcgen05_fence_after();
-        uint32_t su[kCmpCols];
-#pragma unroll
-        for (int h = 0; h < kCmpCols / 32; ++h) tmem_ld_32x32b_x32(tS + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[h * 32]));
-        tmem_wait_ld();
-        float2 pf[kPairs];
-#pragma unroll
-        for (int j4 = 0; j4 < kCmpCols / 4; ++j4) {
-          const float4 l4 = lse_s[j4];
-          const int j = j4 * 4;
-          const float2 t0 = ffma2(make_float2(__uint_as_float(su[j]), __uint_as_float(su[j + 1])), neg_c2, make_float2(l4.x, l4.y));
-          const float2 t1 = ffma2(make_float2(__uint_as_float(su[j + 2]), __uint_as_float(su[j + 3])), neg_c2, make_float2(l4.z, l4.w));
-          if (emulate_pair(j4 * 2)) pf[j4 * 2] = ex2_emul2_neg(t0);
-          else pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
-          if (emulate_pair(j4 * 2 + 1)) pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
-          else pf[j4 * 2 + 1] = make_float2(ex2_approx(-t1.x), ex2_approx(-t1.y));
-        }
-        if (need_mask) {
-#pragma unroll
-          for (int j = 0; j < kPairs; ++j) {
-            const int qi = q0 + 2 * j;
-            const bool row_ok = kv < p.Sk;
-            const bool ok0 = row_ok && (qi < p.Sq) && (!p.causal || kv <= qi + shift);
-            const bool ok1 = row_ok && (qi + 1 < p.Sq) && (!p.causal || kv <= qi + 1 + shift);
-            pf[j].x = ok0 ? pf[j].x : 0.f;
-            pf[j].y = ok1 ? pf[j].y : 0.f;
-          }
-        }
-        {
-          uint32_t pk[kPairs];
-#pragma unroll
-          for (int j = 0; j < kPairs; ++j) pk[j] = pack2<kBf16>(pf[j].x, pf[j].y);
-          if constexpr (kPairs == 16) tmem_st_32x32b_x16(tS, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-          else tmem_st_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-          tmem_wait_st();
-        }
-        tcgen05_fence_before();
-        mbar_arrive(&bars[kPFull]);
-#if FA2_DKDV_CARRY
-        if (kSpill && it > 0) {
-#pragma unroll
-          for (int c = 0; c < kPieces / 2; ++c)
-            st_global_cs_v4(carry_dst + (kPieces / 2 + c) * (kBlk * 16), carry[c * 4], carry[c * 4 + 1], carry[c * 4 + 2], carry[c * 4 + 3]);
-        }
-#endif
-
-        // ---- dS^T = P^T o (dP^T - delta) ----
-        mbar_wait(&bars[kDoFull + ds], dph);  // the delta row travels with dO
-        mbar_wait(&bars[kDpFull], par);
-        tcgen05_fence_after();
-        uint32_t dpu[kCmpCols];
-#pragma unroll
-        for (int h = 0; h < kCmpCols / 32; ++h) tmem_ld_32x32b_x32(tDP + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&dpu[h * 32]));
-        tmem_wait_ld();
-        uint32_t wv[kPairs];
-#pragma unroll
-        for (int j4 = 0; j4 < kCmpCols / 4; ++j4) {
-          const float4 d4 = delta_s[j4];
-          const int j = j4 * 4;
-          const float2 x0 = fsub2(make_float2(__uint_as_float(dpu[j]), __uint_as_float(dpu[j + 1])), make_float2(d4.x, d4.y));
-          const float2 x1 = fsub2(make_float2(__uint_as_float(dpu[j + 2]), __uint_as_float(dpu[j + 3])), make_float2(d4.z, d4.w));
-          const float2 s0 = fmul2(pf[j4 * 2], x0);
-          const float2 s1 = fmul2(pf[j4 * 2 + 1], x1);
-          wv[j4 * 2] = pack2<kBf16>(s0.x, s0.y);
-          wv[j4 * 2 + 1] = pack2<kBf16>(s1.x, s1.y);
-        }
-        mbar_arrive(&bars[kDeltaEmpty + ds]);  // this thread is done with the delta row
-        if constexpr (kPairs == 16) tmem_st_32x32b_x16(tDP, *reinterpret_cast<uint32_t(*)[16]>(&wv[0]));
-        else tmem_st_32x32b_x32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&wv[0]));
-        tmem_wait_st();
-        tcgen05_fence_before();
-        mbar_arrive(&bars[kDsFull]);
-
-        if (kSpill) {
-          const int head = item.head_kv * group + it / m_count;
-          if (j_in_head == 0) prefix = static_cast<int>(ds_tile_prefix(m_start, p.Sq, p.Sk, p.causal));
-          const long long tile = (static_cast<long long>(item.batch) * p.Hq + head) * p.tiles_per_head + prefix + item.nblk;
-          prefix += visible_kv_blocks_of(m, p.Sq, p.Sk, p.causal);
-          uint8_t* dst = static_cast<uint8_t*>(p.ds_spill) + tile * kDsTileBytes + spill_thread_off;
-#if FA2_DKDV_CARRY
-#pragma unroll
-          for (int c = 0; c < kPieces / 2; ++c)
-            st_global_cs_v4(dst + c * (kBlk * 16), wv[c * 4], wv[c * 4 + 1], wv[c * 4 + 2], wv[c * 4 + 3]);
-#pragma unroll
-          for (int j = 0; j < kPieces / 2 * 4; ++j) carry[j] = wv[kPieces / 2 * 4 + j];
-          carry_dst = dst;
-#else
-#pragma unroll
-          for (int c = 0; c < kPieces; ++c)
-            st_global_cs_v4(dst + c * (kBlk * 16), wv[c * 4], wv[c * 4 + 1], wv[c * 4 + 2], wv[c * 4 + 3]);
-#endif
-        }
-      }
-#if FA2_DKDV_CARRY
-      if (kSpill && T > 0) {
-#pragma unroll
-        for (int c = 0; c < kPieces / 2; ++c)
-          st_global_cs_v4(carry_dst + (kPieces / 2 + c) * (kBlk * 16), carry[c * 4], carry[c * 4 + 1], carry[c * 4 + 2], carry[c * 4 + 3]);
-      }
-#endif
-
-      // ---- epilogue: dK * scale and dV -> caller's tensors straight from registers (64 contiguous bytes per thread
-      //      and 32-column chunk); the tensor pipe and the TMA producer are already working on the next item ----
-      constexpr int kChunksPerOut = D / 32;
-      constexpr int kChunks = 2 * kChunksPerOut;
-      constexpr int kMine = (kChunks + kCmpWgs - 1) / kCmpWgs;
-      uint32_t oo[kMine][32];
-      if (T > 0) {
-        mbar_wait(&bars[kDkvFull], tt & 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < kMine; ++cc) {
-          const int chunk = wg + cc * kCmpWgs;
-          if (chunk < kChunks)
-            tmem_ld_32x32b_x32(lane_sel + (chunk < kChunksPerOut ? kTmemDK : kTmemDV) + (chunk % kChunksPerOut) * 32, oo[cc]);
-        }
-        tmem_wait_ld();
-        tcgen05_fence_before();
-        mbar_arrive(&bars[kAccEmpty]);  // the next item's first dV / dK products may overwrite the accumulators
-      } else {
-#pragma unroll
-        for (int cc = 0; cc < kMine; ++cc)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) oo[cc][j] = 0u;
-      }
-#pragma unroll
-      for (int cc = 0; cc < kMine; ++cc) {
-        const int chunk = wg + cc * kCmpWgs;
-        if (chunk < kChunks && kv < p.Sk) {
-          const bool is_dk = chunk < kChunksPerOut;
-          const int col = (chunk % kChunksPerOut) * 32;
-          const float mul = is_dk ? p.softmax_scale : 1.0f;
-          const int64_t* st = is_dk ? p.dk_strides : p.dv_strides;
-          uint16_t* base = reinterpret_cast<uint16_t*>(is_dk ? p.dk : p.dv);
-          uint4* dst = reinterpret_cast<uint4*>(base + item.batch * st[0] + item.head_kv * st[1] + static_cast<int64_t>(kv) * st[2] + col);
-          const uint32_t (&o)[32] = oo[cc];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 v;
-            v.x = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 0]) * mul, __uint_as_float(o[q4 * 8 + 1]) * mul);
-            v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * mul, __uint_as_float(o[q4 * 8 + 3]) * mul);
-            v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * mul, __uint_as_float(o[q4 * 8 + 5]) * mul);
-            v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * mul, __uint_as_float(o[q4 * 8 + 7]) * mul);
-            dst[q4] = v;
-          }
-        }
-      }
-      if (T > 0) {
-        g += T;
-        ++tt;
-      }
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tcgen05_fence_after();
-    tmem_dealloc<512>(0u);
-  }
-}
-
-template <int D, bool kBf16, bool kSpill>
-static cudaError_t launch_bwd_dkdv_persistent_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                                                const CUtensorMap& tdo, const DkdvParams& p, cudaStream_t stream) {
-  auto kernel = fa2_bwd_dkdv_persistent_kernel<D, kBf16, kSpill>;
-  constexpr int smem = DkdvPersistSmem<D>::kBytes;
-  static bool configured[64] = {};
-  static int sm_count[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
-  const int n_items = ((p.Sk + kBlk - 1) / kBlk) * p.Hkv * p.B;
-  int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
-  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas;
-  dim3 grid(n_items < sms ? n_items : sms);
-  kernel<<<grid, kThreads, smem, stream>>>(tq, tk, tv, tdo, p);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
-                                       const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,
-                                       cudaStream_t stream) {
-#define FA2_DKDV_CASE(DD, BF, SP) \
-  if (D == DD && bf16 == BF && spill == SP) return launch_bwd_dkdv_persistent_t<DD, BF, SP>(tq, tk, tv, tdo, p, stream);
-  FA2_DKDV_CASE(128, true, true) FA2_DKDV_CASE(128, true, false) FA2_DKDV_CASE(128, false, true) FA2_DKDV_CASE(128, false, false)
-  FA2_DKDV_CASE(64, true, true) FA2_DKDV_CASE(64, true, false) FA2_DKDV_CASE(64, false, true) FA2_DKDV_CASE(64, false, false)
-#undef FA2_DKDV_CASE
-  return cudaErrorInvalidValue;
-}
-
 template <int D, bool kBf16, bool kSpill, int kExtra>
 static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                                      const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
@@ -1133,17 +643,9 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
   auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kExtra>;
   constexpr int smem = DkdvSmem<D, (kExtra == 1 && D == 128) ? 2 : kQStages, kExtra == 1>::kBytes;
   const CUtensorMap& tbias = p.bias_tma ? *p.bias_map : tq;  // placeholder when the bias is read through plain loads
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kExtra>>(smem); e != cudaSuccess) return e;
   dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv * (kExtra == 3 ? p.kv_split : 1), p.B);
-  kernel<<<grid, kThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, tbias, p);
-  return cudaGetLastError();
+  return launch_pdl(kernel, grid, dim3(kThreads), smem, stream, tq, tk, tv, tdo, tdk, tdv, tbias, p);
 }
 
 cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,

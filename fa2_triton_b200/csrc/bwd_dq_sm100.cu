@@ -497,19 +497,9 @@ static cudaError_t launch_bwd_dq_t(const CUtensorMap& tq, const CUtensorMap& tk,
                                    cudaStream_t stream) {
   auto kernel = fa2_bwd_dq_kernel<D, kBf16, kBias>;
   constexpr int smem = DqSmem<D>::kBytes;
-  static bool configured[64] = {};
-  static int sm_count[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_dq_kernel<D, kBf16, kBias>>(smem); e != cudaSuccess) return e;
   const int n_items = ((p.Sq + kBlk - 1) / kBlk) * p.Hq * p.B;
-  const int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  const int sms = current_sm_count();
   dim3 grid(n_items < sms ? n_items : sms);  // persistent: one CTA per SM, items dealt round-robin
   kernel<<<grid, kDqThreads, smem, stream>>>(tq, tk, tv, tdo, tdq, p);
   return cudaGetLastError();

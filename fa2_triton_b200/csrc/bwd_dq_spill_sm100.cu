@@ -106,6 +106,9 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
   __syncthreads();
   tcgen05_fence_after();
   if (*tmem_slot != 0u) __trap();  // whole-TMEM allocation => base 0 (keeps tcgen05 addresses warp-uniform)
+  // PDL: the prologue above overlapped the tail of the dK/dV kernel; its dS tiles are complete only after this wait
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == kTmaWarp) {
     // ===================================== TMA producer + scheduler ================================
@@ -255,23 +258,11 @@ template <int D, bool kBf16>
 static cudaError_t launch_bwd_dq_spill_t(const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream) {
   auto kernel = fa2_bwd_dq_spill_kernel<D, kBf16>;
   constexpr int smem = DqSpillSmem<D>::kBytes;
-  static bool configured[64] = {};
-  static int sm_count[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_dq_spill_kernel<D, kBf16>>(smem); e != cudaSuccess) return e;
   const int n_items = ((p.Sq + kBlk - 1) / kBlk) * p.Hq * p.B;
-  int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
-  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas;
+  const int sms = current_sm_count();
   dim3 grid(n_items < sms ? n_items : sms);  // persistent: one CTA per SM
-  kernel<<<grid, kThreads, smem, stream>>>(tk, p);
-  return cudaGetLastError();
+  return launch_pdl(kernel, grid, dim3(kThreads), smem, stream, tk, p);
 }
 
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream) {

@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
   constexpr int kRowsPerPass = 256 / kThreadsPerRow;
   constexpr int kPasses = 4;  // rows per thread: all 2 x kPasses 16-byte loads are issued before the first use
   constexpr int kRowsPerBlock = kRowsPerPass * kPasses;
+  pdl_wait();  // O comes from the forward kernel that may still be running (programmatic dependent launch)
+  if (threadIdx.x == 0) pdl_launch_dependents();
   const int head = blockIdx.y, batch = blockIdx.z;
   const int sq_valid = p.seqlens != nullptr ? min(max(p.seqlens[batch], 0), p.Sq) : p.Sq;  // variable-length mode: this sequence's rows
   const int row0 = blockIdx.x * kRowsPerBlock + threadIdx.x / kThreadsPerRow;
@@ -170,17 +172,10 @@ cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream) {
   dim3 grid((p.lse_stride + rows_per_block - 1) / rows_per_block, p.Hq, p.B);
   if (p.D < 8 || p.D > 256 || p.D % 8) return cudaErrorInvalidValue;
   if (p.dq_accum != nullptr && (p.D != dk || dk == 256)) return cudaErrorInvalidValue;  // the accumulator layout needs D in {64, 128}
-  if (dk == 256) {
-    if (bf16) fa2_delta_kernel<256, true><<<grid, 256, 0, stream>>>(p);
-    else fa2_delta_kernel<256, false><<<grid, 256, 0, stream>>>(p);
-  } else if (dk == 128) {
-    if (bf16) fa2_delta_kernel<128, true><<<grid, 256, 0, stream>>>(p);
-    else fa2_delta_kernel<128, false><<<grid, 256, 0, stream>>>(p);
-  } else {
-    if (bf16) fa2_delta_kernel<64, true><<<grid, 256, 0, stream>>>(p);
-    else fa2_delta_kernel<64, false><<<grid, 256, 0, stream>>>(p);
-  }
-  return cudaGetLastError();
+  const dim3 block(256);
+  if (dk == 256) return bf16 ? launch_pdl(fa2_delta_kernel<256, true>, grid, block, 0, stream, p) : launch_pdl(fa2_delta_kernel<256, false>, grid, block, 0, stream, p);
+  if (dk == 128) return bf16 ? launch_pdl(fa2_delta_kernel<128, true>, grid, block, 0, stream, p) : launch_pdl(fa2_delta_kernel<128, false>, grid, block, 0, stream, p);
+  return bf16 ? launch_pdl(fa2_delta_kernel<64, true>, grid, block, 0, stream, p) : launch_pdl(fa2_delta_kernel<64, false>, grid, block, 0, stream, p);
 }
 
 // =================================================================================================
@@ -684,14 +679,7 @@ static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
                                 const BwdParams& p, cudaStream_t stream) {
   auto kernel = fa2_bwd_kernel<D, kBf16, kFusedDq>;
   constexpr int smem = BwdSmem<D>::kBytes;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_kernel<D, kBf16, kFusedDq>>(smem); e != cudaSuccess) return e;
   dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv, p.B);
   kernel<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
   return cudaGetLastError();
@@ -702,8 +690,8 @@ cudaError_t launch_bwd(int D, bool bf16, bool fused_dq, const CUtensorMap& tq, c
                        const BwdParams& p, cudaStream_t stream) {
 #define FA2_BWD_CASE(DD, BF, FU) \
   if (D == DD && bf16 == BF && fused_dq == FU) return launch_bwd_t<DD, BF, FU>(tq, tk, tv, tdo, tdk, tdv, p, stream);
-  FA2_BWD_CASE(128, true, true) FA2_BWD_CASE(128, true, false) FA2_BWD_CASE(128, false, true) FA2_BWD_CASE(128, false, false)
-  FA2_BWD_CASE(64, true, true) FA2_BWD_CASE(64, true, false) FA2_BWD_CASE(64, false, true) FA2_BWD_CASE(64, false, false)
+  // only the fused instantiation is built: dK / dV alone come from bwd_dkdv_sm100.cu
+  FA2_BWD_CASE(128, true, true) FA2_BWD_CASE(128, false, true) FA2_BWD_CASE(64, true, true) FA2_BWD_CASE(64, false, true)
 #undef FA2_BWD_CASE
   return cudaErrorInvalidValue;
 }

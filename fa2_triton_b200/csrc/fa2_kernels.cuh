@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "extras.cuh"
@@ -25,6 +26,31 @@ inline cudaError_t ensure_dynamic_smem(int bytes) {
   if (static_cast<int>(done.size()) <= dev) done.resize(dev + 1, 0);
   done[dev] = 1;
   return cudaSuccess;
+}
+
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled before the previous kernel of the
+// stream has finished, and orders itself behind it with griddepcontrol.wait (ptx.cuh: pdl_wait / pdl_launch_dependents).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// multiprocessor count of the current device (persistent kernels launch one CTA per SM)
+inline int current_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    return 148;
+  return sms;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -172,14 +198,7 @@ struct DkdvParams {
   float softmax_scale;
   float scale_log2;
   int causal;
-  // persistent variant only: work-item counter (0 on entry, re-zeroed by the kernel) and the output tensors, which it
-  // writes straight from registers
-  int* sched;
-  void* dk;
-  void* dv;
-  int64_t dk_strides[3];  // batch, head, seq (elements)
-  int64_t dv_strides[3];
-  int max_ctas;           // > 0: cap on the persistent grid (the rest of the SMs is left to a concurrent kernel)
+  int* zero_word;         // work-item counter of the dQ kernel that follows on the stream: cleared by CTA (0, 0, 0), or nullptr
   BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
   // kBias: a 16-bit bias whose rows TMA can address (16-byte aligned base and strides) is staged tile by tile through
   // shared memory with `bias_map` ((Sk, Sq, 1 | Hq, 1 | B), box 64 x 128); otherwise every thread loads its values itself
@@ -207,9 +226,6 @@ struct DkdvReduceParams {
   int B, Sk, Hkv, D, kv_split;
 };
 cudaError_t launch_dkdv_reduce(bool bf16, const DkdvReduceParams& p, cudaStream_t stream);
-cudaError_t launch_bwd_dkdv_persistent(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
-                                       const CUtensorMap& tv, const CUtensorMap& tdo, const DkdvParams& p,
-                                       cudaStream_t stream);
 cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,
                             const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk,
                             const CUtensorMap& tdv, const DkdvParams& p, cudaStream_t stream);
@@ -225,7 +241,6 @@ struct DqSpillParams {
   int B, Hq, Hkv, Sq, Sk;
   float softmax_scale;
   int causal;
-  int max_ctas;        // > 0: cap on the persistent grid
   int d_actual;        // head dim of the tensors (multiple of 8, <= the kernel's D): columns beyond it are not stored
   const int* seqlens;  // variable-length mode, else nullptr
   const CUtensorMap* vmaps;

@@ -209,6 +209,10 @@ fa2_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // checking it) keeps every tcgen05 address provably warp-uniform: ptxas then feeds UTCHMMA / LDTM / STTM from uniform
   // registers directly instead of wrapping each one in an ELECT + R2UR.BROADCAST "waterfall".
   if (*tmem_slot != 0u) __trap();
+  // PDL: everything above overlapped the tail of the previous kernel of the stream; nothing below may run before it has
+  // completed. The next kernel may be scheduled as soon as every CTA of this grid got here.
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp >= L::kMmaWarp) {
     if constexpr (kTiles == 2) reg_dealloc<L::kRegsIssue>();
@@ -587,8 +591,7 @@ static cudaError_t launch_fwd2_t(const CUtensorMap& tq, const CUtensorMap& tk, c
   FwdParams pp = p;
   pp.n_pairs = (p.Sq + L::kTiles * kBM - 1) / (L::kTiles * kBM);
   dim3 grid(pp.n_pairs, p.Hq, p.B);
-  fa2_fwd2_kernel<D, kBf16, kBias><<<grid, L::kThreads, L::kDynBytes, stream>>>(tq, tk, tv, to, pp);
-  return cudaGetLastError();
+  return launch_pdl(fa2_fwd2_kernel<D, kBf16, kBias>, grid, dim3(L::kThreads), L::kDynBytes, stream, tq, tk, tv, to, pp);
 }
 
 // plain forward (no bias, no dropout) for head-dim instantiations 64 / 128 / 256; with a bias only at 256

@@ -143,3 +143,53 @@ cudaError_t launch_probe(bool bf16, const CUtensorMap& ta, const CUtensorMap& tb
 }
 
 }  // namespace fa2
+
+// ------------------------------------------------------------------------------------------------
+// C entry point of the TEST-ONLY library libfa2_probe.so (not part of libfa2_sm100.so, not in include/fa2_sm100.h):
+//   int fa2_probe_umma(a, b, d, N, K, a_mode, b_mode, dtype /* 16 = fp16, 17 = bf16 */, stream)  -> 0 or an error code
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [rows, cols] row-major 16-bit matrix -> 2-D-in-4-D map (cols, rows, 1, 1), box (64, box_rows), 128-byte swizzle
+int probe_tmap(CUtensorMap* map, const void* ptr, bool bf16, int rows, int cols, int box_rows) {
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return -7;
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), 1, 1};
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(cols) * 2;
+  const cuuint64_t gstride[3] = {row_bytes, row_bytes * rows, row_bytes * rows};
+  const cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(box_rows), 1u, 1u};
+  const cuuint32_t estride[4] = {1u, 1u, 1u, 1u};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(sym)(
+      map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstride,
+      box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+}  // namespace
+
+extern "C" int fa2_probe_umma(const void* a, const void* b, float* d, int N, int K, int a_mode, int b_mode, int dtype,
+                              void* stream) {
+  if (dtype != 16 && dtype != 17) return -2;
+  if ((N != 64 && N != 128) || (K != 64 && K != 128)) return -3;
+  if (a_mode < 0 || a_mode > 4 || b_mode < 0 || b_mode > 1) return -3;
+  if (!a || !b || !d) return -5;
+  const bool bf16 = dtype == 17;
+  CUtensorMap ta, tb;
+  if (int e = probe_tmap(&ta, a, bf16, 128, K, 128)) return e;            // A as [128, K]
+  if (b_mode == 0) {
+    if (int e = probe_tmap(&tb, b, bf16, N, K, N)) return e;              // B^T as [N, K]
+  } else {
+    if (int e = probe_tmap(&tb, b, bf16, K, N, K)) return e;              // B as [K, N]
+  }
+  fa2::ProbeParams p{};
+  p.a = a; p.b = b; p.d = d; p.N = N; p.K = K; p.a_mode = a_mode; p.b_mode = b_mode;
+  return static_cast<int>(fa2::launch_probe(bf16, ta, tb, p, static_cast<cudaStream_t>(stream)));
+}

@@ -128,6 +128,14 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization, see
+// launch_pdl in fa2_kernels.cuh): `pdl_launch_dependents` lets the next kernel of the stream be scheduled as soon as every
+// CTA of this grid has started (its prologue - barrier init, TMEM allocation, tensor-map prefetch - then overlaps this
+// grid's tail); `pdl_wait` blocks until the previous kernel of the stream has COMPLETED and its writes are visible, and
+// must precede every global-memory access of the kernel. Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // named barrier over a subset of the CTA (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -202,13 +210,6 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-#ifdef FA2_OLD_WAIT  // A/B switch: the clock64()-based loop
-  const long long start = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - start > FA2_WATCHDOG_CYCLES) __trap();
-  }
-  return;
-#endif
   uint32_t tries = 0;
   while (!mbar_try_wait_hint(bar, parity)) {
     if (++tries > FA2_WATCHDOG_TRIES) __trap();

@@ -122,25 +122,32 @@ def sharded_attention(q: Tensor, k: Tensor, v: Tensor, world_size: int, rank: in
     return results
 
 
-def gather_for_verification(local: Tensor, global_shape: Sequence[int], blocks, group=None, heads_per_unit: int = 1):
+def gather_for_verification(local: Tensor, global_shape: Sequence[int], blocks, group=None, heads_per_unit: int = 1,
+                            dtype: Optional[torch.dtype] = None, device=None):
     """All-gather every rank's output blocks into a full ``global_shape`` tensor on every rank. Verification only -
     this is the single place the multi-GPU path uses a collective.
 
     ``local`` is a list of tensors matching ``blocks`` (this rank's ``(b0, b1, h0, h1)`` blocks, kv-head units;
-    ``heads_per_unit`` = Hq / Hkv for q-like tensors, 1 for kv-like)."""
+    ``heads_per_unit`` = Hq / Hkv for q-like tensors, 1 for kv-like). ``dtype`` / ``device`` of the gathered tensor:
+    taken from ``local`` when this rank has blocks; a rank without work MUST be told (every rank's broadcast buffers
+    have to agree in dtype with the senders'), otherwise it raises."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    full = torch.zeros(*global_shape, dtype=local[0].dtype, device=local[0].device) if local else None
+    if local:
+        dtype = local[0].dtype if dtype is None else dtype
+        device = local[0].device if device is None else device
+    if dtype is None:
+        raise ValueError("gather_for_verification: a rank without blocks needs the dtype of the gathered tensor")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    full = torch.zeros(*global_shape, dtype=dtype, device=device)
     meta = [None] * world
     dist.all_gather_object(meta, [tuple(b) for b in blocks], group=group)
-    if full is None:  # a rank without work still has to take part in the broadcasts
-        ref_dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-        full = torch.zeros(*global_shape, device=ref_dev)
     for src in range(world):
         for i, (b0, b1, h0, h1) in enumerate(meta[src]):
             view = full[b0:b1, :, h0 * heads_per_unit:h1 * heads_per_unit]
-            buf = local[i].contiguous() if src == dist.get_rank(group) else torch.empty_like(view.contiguous())
+            buf = local[i].to(dtype).contiguous() if src == dist.get_rank(group) else torch.empty_like(view.contiguous())
             dist.broadcast(buf, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
             view.copy_(buf)
     return full

@@ -31,10 +31,13 @@
  *     fa2_sm100_last_error() returns a thread-local description of the last failure.
  *   - thread safety: calls may be made concurrently from different host threads.
  *
- * Supported in this build: head dims D = 8, 16, ..., 128 (the kernels exist for 64 and 128; a smaller multiple of 8 runs
- * in the next one, TMA zero-filling the missing columns - the reference pads to a power of two inside its kernels the
- * same way, src/forward/caller.py:77-78; the fused backward modes 0 and 2 need 64 or 128); Hq % Hkv == 0; any Sq, Sk >= 1;
- * base pointers 16-byte aligned and every stride a multiple of 8 elements (TMA requirement).
+ * Supported in this build: head dims D = 8, 16, ..., 256 (the kernels exist for 64, 128 and 256; a smaller multiple of 8
+ * runs in the next one, TMA zero-filling the missing columns - the reference pads to a power of two inside its kernels the
+ * same way, src/forward/caller.py:77-78). Above 128: forward without dropout; backward through one deterministic path
+ * (`deterministic` 1, 3, 4 or 5; no variable-length mode). The fused backward modes 0 and 2 need D = 64 or 128.
+ * Hq % Hkv == 0; any Sq, Sk >= 1; base pointers 16-byte aligned and every stride a multiple of 8 elements (TMA
+ * requirement). A stride of 0 is accepted only for a dimension of extent 1: an expanded (broadcast) tensor must be
+ * materialised by the caller (FA2_E_BAD_SHAPE otherwise) - the Python host shim does so.
  */
 #ifndef FA2_SM100_H_
 #define FA2_SM100_H_
@@ -46,7 +49,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 10
+#define FA2_SM100_ABI_VERSION 11
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -202,13 +205,6 @@ int fa2_sm100_dq_convert(const void* workspace, void* dq,
  * slice of a [B, S, H, D] tensor without packing it first (fa2_triton_b200/host_api.py; bench.py's `e2e`). */
 int fa2_sm100_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
                            size_t rows, int to_device, void* stream);
-
-/* Hardware probe used by the test-suite: D[128, N] = A * B through one UMMA operand path.
- * a_mode 0: A [128, K] row-major (smem, K-major)   1: A given transposed [K, 128] (smem, MN-major)
- *        2: A [128, K] row-major staged in tensor memory
- * b_mode 0: B given as [N, K] row-major (K-major)  1: B given as [K, N] row-major (MN-major) */
-int fa2_sm100_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_mode, int b_mode,
-                               int dtype, void* stream);
 
 #ifdef __cplusplus
 }

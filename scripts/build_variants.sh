@@ -6,12 +6,12 @@
 set -e
 cd "$(dirname "$0")/../fa2_triton_b200/csrc"
 mkdir -p ../../variants
-ALL="api fwd_sm100 fwd2_sm100 bwd_sm100 bwd_dkdv_sm100 bwd_dq_sm100 bwd_dq_spill_sm100 bwd256_sm100 varlen_sm100 probe_sm100"
+ALL="api fwd_sm100 fwd2_sm100 bwd_sm100 bwd_dkdv_sm100 bwd_dq_sm100 bwd_dq_spill_sm100 bwd256_sm100 varlen_sm100"
 while [ $# -gt 2 ]; do
   name=$1; files=$2; flags=$3; shift 3
   d=../../variants/obj_$name; mkdir -p $d
   objs=""
-  for f in $ALL; do
+  for f in $ALL; do  # (probe_sm100 is a test-only library of its own)
     if echo " $files " | grep -q " $f.cu "; then
       nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $flags -c $f.cu -o $d/$f.o 2> $d/$f.log &
       objs="$objs $d/$f.o"

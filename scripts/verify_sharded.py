@@ -25,7 +25,7 @@ for block, qs, ks, vs, dos in shard.shard_views(q, k, v, world, rank, do):
     dq_, dk_, dv_ = torch.autograd.grad(o, (qq, kk, vv), dos)
     blocks.append(block); outs.append(o.detach()); dqs.append(dq_); dks.append(dk_); dvs.append(dv_)
 grp = Hq // Hkv
-full = [shard.gather_for_verification(t, shp, blocks, heads_per_unit=hpu)
+full = [shard.gather_for_verification(t, shp, blocks, heads_per_unit=hpu, dtype=q.dtype, device=dev)
         for t, shp, hpu in ((outs, q.shape, grp), (dqs, q.shape, grp), (dks, k.shape, 1), (dvs, k.shape, 1))]
 if rank == 0:
     qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))

@@ -140,34 +140,6 @@ def test_spill_falls_back_to_recompute_when_the_workspace_is_capped(monkeypatch)
     assert_close_16("dQ", dq1, dq5.float())
 
 
-def test_persistent_dkdv_kernel_matches_the_default(monkeypatch):
-    """FA2_SM100_DKDV_PERSISTENT=1 (read once per process, so: a subprocess) selects the persistent dK/dV kernel; it
-    must give bit-identical dK / dV / dQ (same arithmetic, same order)."""
-    import subprocess, sys, textwrap
-    code = textwrap.dedent("""
-        import sys, torch
-        sys.path.insert(0, %r); sys.path.insert(0, %r)
-        import fa2_triton_b200 as fa2
-        from fa2_test_utils import generate_test_data
-        outs = []
-        for shape in ((2, 640, 640, 4, 2, 128, True), (1, 300, 1000, 2, 2, 64, True), (2, 384, 129, 2, 2, 128, True), (1, 1000, 1000, 2, 2, 64, False)):
-            B, Sq, Sk, Hq, Hkv, D, causal = shape
-            q, k, v, do = generate_test_data(B, Sq, Sk, Hq, Hkv, D, torch.bfloat16, "cuda:0", 3)
-            q, k, v = (t.requires_grad_(True) for t in (q, k, v))
-            o = fa2.flash_attn_func(q, k, v, causal=causal)
-            outs += [g.cpu() for g in torch.autograd.grad(o, (q, k, v), do)]
-        torch.save(outs, sys.argv[1])
-    """) % (str(__import__("pathlib").Path(__file__).resolve().parent.parent), str(__import__("pathlib").Path(__file__).resolve().parent))
-    import os, tempfile
-    res = []
-    for flag in ("0", "1"):
-        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
-            env = dict(os.environ, FA2_SM100_DKDV_PERSISTENT=flag)
-            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
-            res.append(torch.load(f.name))
-    for a, b in zip(*res):
-        assert torch.equal(a, b)
-
 
 def test_backward_masking_is_exact():
     """Causally hidden keys and the padding past Sk/Sq must not leak into any gradient."""

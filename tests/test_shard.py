@@ -65,7 +65,8 @@ def _worker(rank, world, port, results):
         attn = lambda a, b, c, causal, softmax_scale: er.flash_attn_reference(a, b, c, causal=causal, softmax_scale=softmax_scale)
         out = shard.sharded_attention(q, k, v, world, rank, causal=True, attn=attn)
         blocks = [b for b, _ in out]
-        full = shard.gather_for_verification([o for _, o in out], q.shape, blocks, heads_per_unit=Hq // Hkv)
+        full = shard.gather_for_verification([o for _, o in out], q.shape, blocks, heads_per_unit=Hq // Hkv, dtype=q.dtype,
+                                             device=q.device)
         ref = er.flash_attn_reference(q, k, v, causal=True)
         err = float((full - ref).abs().max())
         # the per-call extras travel with the slices: a per-(batch, head) bias and a right-padded attention mask
@@ -76,7 +77,8 @@ def _worker(rank, world, port, results):
             attn2 = lambda a, b, c, causal, softmax_scale, attention_mask=None, attention_bias=None: er.flash_attn_reference(
                 a, b, c, causal=causal, softmax_scale=softmax_scale, padding_mask=attention_mask, attn_bias=attention_bias)
             out2 = shard.sharded_attention(q, k, v, world, rank, causal=True, attn=attn2, **kw_in)
-            full2 = shard.gather_for_verification([o for _, o in out2], q.shape, [b for b, _ in out2], heads_per_unit=Hq // Hkv)
+            full2 = shard.gather_for_verification([o for _, o in out2], q.shape, [b for b, _ in out2], heads_per_unit=Hq // Hkv,
+                                                  dtype=q.dtype, device=q.device)
             err = max(err, float((full2 - er.flash_attn_reference(q, k, v, causal=True, **kw_ref)).abs().max()))
         results[rank] = err
     finally:
