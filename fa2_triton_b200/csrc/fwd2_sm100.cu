@@ -92,6 +92,8 @@ struct Fwd2Cfg {
 #else
   static constexpr int kEmul = D == 64 ? 1 : 0;
 #endif
+  // exponentials formed with the current reference maximum while the block maximum is still being taken (softmax loop)
+  static constexpr bool kSpeculate = D == 64;
 };
 
 // number of 64-key half-blocks query tile [row0, row0 + 128) has to visit
@@ -447,66 +449,99 @@ fa2_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int e = 0; e < kHB; ++e) s[e] = (col0 + e <= limit) ? s[e] : -INFINITY;
       }
 
-      // block maximum: 3-input maxima (FMNMX3), four independent chains
-      float mx[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) mx[e] = fmax3(s[e], s[e + 4], s[e + 8]);
-#pragma unroll
-      for (int e = 12; e < kHB - 4; e += 8) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) mx[q] = fmax3(mx[q], s[e + q], s[e + q + 4]);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) mx[q] = fmaxf(mx[q], s[kHB - 4 + q]);
-      const float mb = fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]) * c;
-
-      // lazy rescale: only move the reference max when the block max exceeds it by > 2^8
-      const bool need = mb > m_ref + kRescaleThreshold;
-      float alpha = 1.f;
-      if (need) {
-        alpha = ex2_approx(m_ref - mb);  // m_ref == -inf -> 0
-        m_ref = mb;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare. O must be at rest: P V(j-1) - issued after this thread handed over P(j-1) - has to have retired
-        mbar_wait(&pv_done[t], (j - 1) & 1);
-        tcgen05_fence_after();
-#pragma unroll 1
-        for (int cidx = 0; cidx < D / 16; ++cidx) {
-          uint32_t o[16];
-          tmem_ld_32x32b_x16(tO + cidx * 16, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-          tmem_st_32x32b_x16(tO + cidx * 16, o);
-        }
-        tmem_wait_st();
-      }
-      l *= alpha;
-
-      if (r == 0) FA2_STAMP(t, j, 3);
-      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-      const float2 neg_m2 = make_float2(neg_m, neg_m);
       uint32_t pk[kHB / 2];
       float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      auto exp_block = [&](auto emulate) {
-#pragma unroll
-        for (int e = 0; e < kHB; e += 2) {
-          const float2 x2 = ffma2(make_float2(s[e], s[e + 1]), c2, neg_m2);
-          float2 p2;
-          if (decltype(emulate)::value && ((e / 2) % 4) < L::kEmul) {
-            p2 = ex2_emul2(x2);
-          } else {
-            p2.x = ex2_approx(x2.x);
-            p2.y = ex2_approx(x2.y);
-          }
-          ls[(e / 2) % 2] = fadd2(ls[(e / 2) % 2], p2);
-          pk[e / 2] = pack2<kBf16>(p2.x, p2.y);
+      // one pair of probabilities: p = 2^(s c - m), added to the row sum in fp32, rounded to 16 bits for P V
+      auto exp_pair = [&](int e, const float2 neg_m2, float2 (&acc)[2], auto emulate) {
+        const float2 x2 = ffma2(make_float2(s[e], s[e + 1]), c2, neg_m2);
+        float2 p2;
+        if (decltype(emulate)::value && ((e / 2) % 4) < L::kEmul) {
+          p2 = ex2_emul2(x2);
+        } else {
+          p2.x = ex2_approx(x2.x);
+          p2.y = ex2_approx(x2.y);
         }
+        acc[(e / 2) % 2] = fadd2(acc[(e / 2) % 2], p2);
+        pk[e / 2] = pack2<kBf16>(p2.x, p2.y);
       };
-      // masked half-blocks (and every half-block with a bias, which may hold -inf) keep all exponentials on the MUFU:
-      // exact 0 for -inf scores
-      if (need_mask || kBias) exp_block(std::false_type{}); else exp_block(std::true_type{});
+
+      // Fast path at head dim 64 (every half-block but the first and the masked ones): the exponentials do not wait for
+      // the block maximum. The reference maximum only moves when a block exceeds it by 2^8 (lazy rescale), which after
+      // the first blocks of a row is rare, so the probabilities are formed with the CURRENT reference while the maximum
+      // is taken in the same instruction stream - the maxima fill the issue slots the MUFU leaves - and are kept unless
+      // some row of the warp does need a new reference (then the block is redone below, from the untouched scores).
+      // Same arithmetic either way. Measured (profiles/r02_experiments.txt): S = 16384, D = 64 non-causal 2.98-3.06 ->
+      // 2.83-2.86 ms; at head dim 128, where the tensor pipe (1280 of the ~1600 cycles per half-block) and not the MUFU
+      // is the tighter resource, 0.500 -> 0.520 ms, so it is off there.
+      bool kept = false;
+      if constexpr (!kBias && L::kSpeculate) {
+        if (!need_mask && j > 0) {
+          const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+          const float2 neg_m2 = make_float2(neg_m, neg_m);
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int e = 0; e < kHB; e += 8) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mx[q] = fmax3(mx[q], s[e + q], s[e + q + 4]);
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) exp_pair(e + u, neg_m2, ls, std::true_type{});
+          }
+          const float mb = fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]) * c;
+          kept = !__any_sync(0xffffffffu, mb > m_ref + kRescaleThreshold);
+        }
+      }
+      if (!kept) {
+        // block maximum: 3-input maxima (FMNMX3), four independent chains
+        float mx[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mx[e] = fmax3(s[e], s[e + 4], s[e + 8]);
+#pragma unroll
+        for (int e = 12; e < kHB - 4; e += 8) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mx[q] = fmax3(mx[q], s[e + q], s[e + q + 4]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mx[q] = fmaxf(mx[q], s[kHB - 4 + q]);
+        const float mb = fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]) * c;
+
+        // lazy rescale: only move the reference max when the block max exceeds it by > 2^8
+        const bool need = mb > m_ref + kRescaleThreshold;
+        float alpha = 1.f;
+        if (need) {
+          alpha = ex2_approx(m_ref - mb);  // m_ref == -inf -> 0
+          m_ref = mb;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          // rare. O must be at rest: P V(j-1) - issued after this thread handed over P(j-1) - has to have retired
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tcgen05_fence_after();
+#pragma unroll 1
+          for (int cidx = 0; cidx < D / 16; ++cidx) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tO + cidx * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_32x32b_x16(tO + cidx * 16, o);
+          }
+          tmem_wait_st();
+        }
+        l *= alpha;
+
+        if (r == 0) FA2_STAMP(t, j, 3);
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+        const float2 neg_m2 = make_float2(neg_m, neg_m);
+        ls[0] = ls[1] = make_float2(0.f, 0.f);
+        // masked half-blocks (and every half-block with a bias, which may hold -inf) keep all exponentials on the MUFU:
+        // exact 0 for -inf scores
+        if (need_mask || kBias) {
+#pragma unroll
+          for (int e = 0; e < kHB; e += 2) exp_pair(e, neg_m2, ls, std::false_type{});
+        } else {
+#pragma unroll
+          for (int e = 0; e < kHB; e += 2) exp_pair(e, neg_m2, ls, std::true_type{});
+        }
+      }
       l += (ls[0].x + ls[1].x) + (ls[0].y + ls[1].y);
       if (r == 0) FA2_STAMP(t, j, 4);
 

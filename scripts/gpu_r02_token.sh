@@ -1,0 +1,9 @@
+#!/bin/bash
+# Round 2: MUFU token between the two softmax warps of a scheduler (fwd2_sm100.cu) - parity, then A/B timing in one call.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_forward_gpu.py tests/test_varlen_headdim_gpu.py tests/test_triton_golden_gpu.py -m gpu -q -x --timeout 300 > gpurun_out/fwd_tests.log 2>&1
+echo "fwd tests exit $?"; tail -3 gpurun_out/fwd_tests.log
+for rep in 1 2; do
+  echo "== no token"; FWD_TIMES_CASES=4 FA2_SM100_LIB=variants/lib_notoken.so timeout 300 python scripts/fwd_times.py 2>&1 | tee -a gpurun_out/fwd_times_notoken.txt
+  echo "== token"; FWD_TIMES_CASES=4 timeout 300 python scripts/fwd_times.py 2>&1 | tee -a gpurun_out/fwd_times_token.txt
+done

@@ -91,6 +91,14 @@ int main() {
   run<true, 128, 1, true, false>("TS N=128 MN-major B, 1 accumulator", d);
   run<true, 128, 2, true, false>("TS N=128 MN-major B, 2 accumulators", d);
   run<true, 128, 1, true, true>("TS N=128 MN-major B, same operands", d);
+  run<false, 64, 1, false, false>("SS N=64 K-major B, 1 accumulator", d);
+  run<false, 64, 2, false, false>("SS N=64 K-major B, 2 accumulators", d);
+  run<false, 64, 1, false, true>("SS N=64 K-major B, same operands", d);
+  run<true, 64, 1, false, false>("TS N=64 K-major B, 1 accumulator", d);
+  run<true, 64, 1, true, false>("TS N=64 MN-major B, 1 accumulator", d);
+  run<false, 32, 1, false, false>("SS N=32 K-major B, 1 accumulator", d);
+  run<false, 96, 1, false, false>("SS N=96 K-major B, 1 accumulator", d);
+  run<false, 192, 1, false, false>("SS N=192 K-major B, 1 accumulator", d);
   run<false, 256, 1, false, false>("SS N=256 K-major B, 1 accumulator", d);
   run<true, 256, 1, false, false>("TS N=256 K-major B, 1 accumulator", d);
   return 0;
