@@ -349,6 +349,12 @@ def main():
         if args.atomic:
             dom = "fa2_bwd_kernel<fused dQ> + fa2_dq_convert_kernel"
             seq.append((dom, lambda: call_bwd(_lib.DQ_ATOMIC), 2.5 * f_fwd, None))
+        elif D <= 64:
+            # head dim 64: the deterministic backward recomputes S and dP in its dQ kernel instead of spilling dS
+            # (fa2_triton_b200/backward.py); algorithmic FLOPs stay 4 + 1 products, the dQ kernel executes 3
+            dom = "fa2_bwd_dkdv_kernel"
+            seq.append((dom, lambda: call_bwd(_lib.DQ_NONE), 2.0 * f_fwd, None))
+            seq.append(("fa2_bwd_dq_kernel (recomputing)", lambda: call_bwd(_lib.DQ_ONLY), 0.5 * f_fwd, None))
         else:
             # S, dP, dV, dK are the dK/dV kernel's products (it also spills dS); the dQ kernel's one product is dS K
             dom = "fa2_bwd_dkdv_kernel<spill>"

@@ -28,6 +28,12 @@
 //   issue   : warp 0 MMA issuer, warp 1 TMA producer, warps 2-3 idle
 // TMEM (512 columns): S^T / P^T [0,128) | dP^T / dS^T [128,256) | dV [256,256+D) | dK [384,384+D)
 // Tensor-pipe order per query block i:  dV(i) | S^T(i+1) | dK(i) | dP^T(i+1)
+// Head dim 64 (dV and dK are 64 columns each): S^T is DOUBLE-BUFFERED - S^T / P^T [0,128) and [128,256) | dP^T / dS^T
+// [256,384) | dV [384,448) | dK [448,512), order  dV(i) | S^T(i+2) | dK(i) | dP^T(i+1)  - so that the compute warps find the
+// scores of block i + 1 waiting when they are done with block i. At this head dim the four products of a block pair take
+// 1024 tensor cycles against ~1300 issue cycles of exponentials and dS arithmetic on every scheduler: the compute warps
+// are the bottleneck, and with one S^T buffer they also sat out the round trip P^T(i) -> dV(i), S^T(i+1) in every
+// iteration (2350 cycles per block pair at S = 16384).
 #include "fa2_kernels.cuh"
 #include "ptx.cuh"
 
@@ -63,15 +69,27 @@ constexpr int kMmaWarp = kCmpWgs * 4, kTmaWarp = kMmaWarp + 1;
 constexpr int kRegsCmp = kCmpWgs == 4 ? 104 : 208;
 constexpr int kRegsIssue = kCmpWgs == 4 ? 64 : 88;
 constexpr int kQStages = 3;   // Q (+LSE) ring: Q(i) lives from S^T(i) to dK(i), and Q(i+1) is wanted right after dV(i)
+constexpr int kQStagesDbl = 4;  // head dim 64, double-buffered S^T: Q(i+2) is wanted right after dV(i)
 constexpr int kDoStages = 2;  // dO (+delta) ring
-// how many of every 4 pairs of exponentials are evaluated on the FMA pipes (ex2_emul2_neg) instead of the MUFU
-// (measured optimum; scripts/build_variants.sh rebuilds with another value for A/B runs)
+// the bias variant at head dim 128 gives its third Q stage to the bias tile
+__host__ __device__ constexpr int q_stages(int D, int extra) {
+  return D == 64 ? kQStagesDbl : (extra == 1 && D == 128) ? 2 : kQStages;
+}
+// How many of every 4 pairs of exponentials are evaluated on the FMA pipes (ex2_emul2_neg) instead of the MUFU. Measured
+// (scripts/build_variants.sh rebuilds with another value for A/B runs): head dim 128, S = 4096 causal, sustained: 0/4
+// 1.096 ms, 1/4 1.063, 2/4 1.02-1.03, 3/4 1.08, 4/4 1.14; head dim 64 with the double-buffered S^T, S = 16384: 0/4
+// 3.90-3.96 ms, 1/4 4.02, 2/4 4.10-4.20, 3/4 4.28-4.42 - there the issue slots, not the MUFU, are what the compute warps
+// run out of, and an emulated pair costs ~12 instructions against 2.
 #ifndef FA2_DKDV_EMUL
 #define FA2_DKDV_EMUL 2
 #endif
+#ifndef FA2_DKDV_EMUL_D64
+#define FA2_DKDV_EMUL_D64 0
+#endif
+template <int D>
 __host__ __device__ constexpr bool emulate_pair(int q) {
-  return FA2_DKDV_EMUL == 4 ? true : FA2_DKDV_EMUL == 3 ? (q % 4 != 0) : FA2_DKDV_EMUL == 2 ? (q % 2 == 1)
-       : FA2_DKDV_EMUL == 1 ? (q % 4 == 3) : false;
+  constexpr int n = D == 64 ? FA2_DKDV_EMUL_D64 : FA2_DKDV_EMUL;
+  return n == 4 ? true : n == 3 ? (q % 4 != 0) : n == 2 ? (q % 2 == 1) : n == 1 ? (q % 4 == 3) : false;
 }
 
 // kQS: stages of the Q ring; kBiasTile: room for one [128 queries x 128 keys] 16-bit tile of the attention bias (the
@@ -92,26 +110,30 @@ struct DkdvSmem {
   static constexpr int kLseOff = kDOOff + kDoStages * kTileBytes;   // kQS x 512 B
   static constexpr int kDeltaOff = kLseOff + kQS * kBlk * 4;        // kDoStages x 512 B
   static constexpr int kBarOff = kDeltaOff + kDoStages * kBlk * 4;
-  static constexpr int kNumBars = 20;
+  static constexpr int kNumBars = 24;
   static constexpr int kTmemSlotOff = kBarOff + kNumBars * 8;
   static constexpr int kBytes = kTmemSlotOff + 16;
   static_assert(kBytes <= 232448, "dK/dV kernel smem budget exceeded");
 };
 
-enum DkdvBar {
-  kKvFull = 0,
-  kQFull = 1,     // [3]
-  kQEmpty = 4,    // [3]
-  kDoFull = 7,    // [2]
-  kDoEmpty = 9,   // [2]
-  kSFull = 11,    // S^T(i) is in tensor memory
-  kPFull = 12,    // P^T(i) is in tensor memory (over S^T)
-  kDpFull = 13,
-  kDsFull = 14,   // dS^T(i) is in tensor memory (over dP^T)
-  kDkvFull = 15,
-  kDeltaEmpty = 16,  // [2] every compute thread has read the delta row in this slot
-  kBiasFull = 18,    // bias variant: the bias tile of this iteration has landed
-  kBiasEmpty = 19,   // ... and every compute thread has read its values
+// mbarrier slots (kQS = stages of the Q ring)
+template <int kQS>
+struct DkdvBars {
+  static constexpr int kKvFull = 0;
+  static constexpr int kQFull = 1;                // [kQS]
+  static constexpr int kQEmpty = kQFull + kQS;    // [kQS]
+  static constexpr int kDoFull = kQEmpty + kQS;   // [2]
+  static constexpr int kDoEmpty = kDoFull + 2;    // [2]
+  static constexpr int kSFull = kDoEmpty + 2;     // [2] S^T(i) is in tensor memory (buffer i & 1 when double-buffered, else slot 0)
+  static constexpr int kPFull = kSFull + 2;       // [2] P^T(i) is in tensor memory (over S^T)
+  static constexpr int kDpFull = kPFull + 2;
+  static constexpr int kDsFull = kDpFull + 1;     // dS^T(i) is in tensor memory (over dP^T)
+  static constexpr int kDkvFull = kDsFull + 1;
+  static constexpr int kDeltaEmpty = kDkvFull + 1;  // [2] every compute thread has read the delta row in this slot
+  static constexpr int kBiasFull = kDeltaEmpty + 2;   // bias variant: the bias tile of this iteration has landed
+  static constexpr int kBiasEmpty = kBiasFull + 1;    // ... and every compute thread has read its values
+  static constexpr int kCount = kBiasEmpty + 1;
+  static_assert(kCount <= 24, "more mbarriers than DkdvSmem reserves");
 };
 
 // streaming 16-byte store (written once, read once by the dQ kernel: evict first)
@@ -130,12 +152,21 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                     const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
                     const __grid_constant__ CUtensorMap tmap_bias, const DkdvParams p) {
-  // the bias variant at head dim 128 gives its third Q stage to the bias tile
-  constexpr int kQS = (kExtra == 1 && D == 128) ? 2 : kQStages;
+  constexpr bool kDbl = D == 64;  // double-buffered S^T (see the top of the file)
+  constexpr int kQS = q_stages(D, kExtra);
   using L = DkdvSmem<D, kQS, kExtra == 1>;
+  using Bar = DkdvBars<kQS>;
+  constexpr int kKvFull = Bar::kKvFull, kQFull = Bar::kQFull, kQEmpty = Bar::kQEmpty, kDoFull = Bar::kDoFull,
+                kDoEmpty = Bar::kDoEmpty, kSFull = Bar::kSFull, kPFull = Bar::kPFull, kDpFull = Bar::kDpFull,
+                kDsFull = Bar::kDsFull, kDkvFull = Bar::kDkvFull, kDeltaEmpty = Bar::kDeltaEmpty;
+  [[maybe_unused]] constexpr int kBiasFull = Bar::kBiasFull, kBiasEmpty = Bar::kBiasEmpty;
   constexpr int kSub = D / 64;
   constexpr int kSubBytes = kBlk * 128;  // [128 rows x 64 x 16-bit]
-  constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
+  constexpr uint32_t kTmemS = 0, kTmemDP = kDbl ? 256 : 128, kTmemDV = kDbl ? 384 : 256, kTmemDK = kDbl ? 448 : 384;
+  constexpr int kAhead = kDbl ? 2 : 1;  // S^T(i + kAhead) is issued right after dV(i)
+  // S^T buffer of query block i, the barrier slot that goes with it and the parity of its i-th use
+  auto sbuf = [](int i) { return kDbl ? (i & 1) : 0; };
+  auto spar = [](int i) { return static_cast<uint32_t>(kDbl ? (i >> 1) & 1 : i & 1); };
   constexpr int kPairs = kCmpCols / 2;
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -211,8 +242,10 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       mbar_init(&bars[kBiasFull], 1);
       mbar_init(&bars[kBiasEmpty], kCmpThreads);
-      mbar_init(&bars[kSFull], 1);
-      mbar_init(&bars[kPFull], kCmpThreads);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars[kSFull + b], 1);
+        mbar_init(&bars[kPFull + b], kCmpThreads);
+      }
       mbar_init(&bars[kDpFull], 1);
       mbar_init(&bars[kDsFull], kCmpThreads);
       mbar_init(&bars[kDkvFull], 1);
@@ -245,9 +278,24 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tma_load_4d(sK + j * kSubBytes, mk, &bars[kKvFull], j * 64, kv0, head_kv_src, bc);
           tma_load_4d(sV + j * kSubBytes, mv, &bars[kKvFull], j * 64, kv0, head_kv_src, bc);
         }
+        // Q(i) + its LSE row: released by dK(i - kQS)
+        auto load_q = [&](int i) {
+          const int qs = i % kQS;
+          const uint32_t qph = (i / kQS) & 1;
+          const int head = head_kv * group + i / m_count;
+          const int m = m_start + i % m_count;
+          const int64_t row_off = (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
+          mbar_wait(&bars[kQEmpty + qs], qph ^ 1);
+          mbar_arrive_expect_tx(&bars[kQFull + qs], L::kTileBytes + kBlk * 4);
+          for (int j = 0; j < kSub; ++j)
+            tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, mq, &bars[kQFull + qs], j * 64, m * kBlk, head, bc);
+          bulk_load_1d(sLse + qs * kBlk, p.lse + row_off, kBlk * 4, &bars[kQFull + qs]);
+        };
+        // the Q ring runs kAhead - 1 blocks ahead of the dO ring (double-buffered S^T: Q(i + 2) is wanted right after dV(i))
+        for (int i = 0; i < kAhead - 1 && i < T; ++i) load_q(i);
         for (int it = 0; it < T; ++it) {
-          const int qs = it % kQS, ds = it % kDoStages;
-          const uint32_t qph = (it / kQS) & 1, dph = (it / kDoStages) & 1;
+          const int ds = it % kDoStages;
+          const uint32_t dph = (it / kDoStages) & 1;
           const int head = head_kv * group + it / m_count;
           const int m = m_start + it % m_count;
           const int64_t row_off = (static_cast<int64_t>(batch) * p.Hq + head) * p.lse_stride + m * kBlk;
@@ -260,12 +308,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                             p.bias_head_mul * head, p.bias_batch_mul * batch);
             }
           }
-          // Q(it) + its LSE row: released by dK(it - 3)
-          mbar_wait(&bars[kQEmpty + qs], qph ^ 1);
-          mbar_arrive_expect_tx(&bars[kQFull + qs], L::kTileBytes + kBlk * 4);
-          for (int j = 0; j < kSub; ++j)
-            tma_load_4d(sQ + qs * L::kTileBytes + j * kSubBytes, mq, &bars[kQFull + qs], j * 64, m * kBlk, head, bc);
-          bulk_load_1d(sLse + qs * kBlk, p.lse + row_off, kBlk * 4, &bars[kQFull + qs]);
+          if (it + kAhead - 1 < T) load_q(it + kAhead - 1);
           // dO(it) + its delta row: released by dV(it - 2) and by the readers of delta(it - 2)
           mbar_wait(&bars[kDoEmpty + ds], dph ^ 1);
           mbar_wait(&bars[kDeltaEmpty + ds], dph ^ 1);
@@ -315,6 +358,12 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tcgen05_fence_after();
         issue_kmajor(kTmemS, k_kmaj, q_kmaj);  // S^T(0) = K Q(0)^T
         umma_commit(&bars[kSFull]);
+        if (kDbl && T > 1) {  // S^T(1) into the second buffer
+          mbar_wait(&bars[kQFull + 1], 0);
+          tcgen05_fence_after();
+          issue_kmajor(kTmemS + 128, k_kmaj, advance(q_kmaj, L::kTileBytes));
+          umma_commit(&bars[kSFull + 1]);
+        }
         mbar_wait(&bars[kDoFull + 0], 0);
         tcgen05_fence_after();
         issue_kmajor(kTmemDP, v_kmaj, do_kmaj);  // dP^T(0) = V dO(0)^T
@@ -322,22 +371,24 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
         for (int it = 0; it < T; ++it) {
           const uint32_t par = it & 1;
-          const int qs = it % kQS, qsn = (it + 1) % kQS;
+          const int qs = it % kQS, qsn = (it + kAhead) % kQS;
           const int ds = it % kDoStages, dsn = (it + 1) % kDoStages;
-          const uint32_t qphn = ((it + 1) / kQS) & 1, dphn = ((it + 1) / kDoStages) & 1;
+          const uint32_t qphn = ((it + kAhead) / kQS) & 1, dphn = ((it + 1) / kDoStages) & 1;
+          const uint32_t tmem_s = kTmemS + sbuf(it) * 128;
           // dV += P^T(it) dO(it)
-          mbar_wait(&bars[kPFull], par);
+          mbar_wait(&bars[kPFull + sbuf(it)], spar(it));
           tcgen05_fence_after();
           FA2_STAMP(2, it, 0);
-          issue_acc(kTmemDV, kTmemS, advance(do_mn, ds * L::kTileBytes), it > 0);
+          issue_acc(kTmemDV, tmem_s, advance(do_mn, ds * L::kTileBytes), it > 0);
           umma_commit(&bars[kDoEmpty + ds]);  // dO(it) has fed dP(it) and dV(it)
           FA2_STAMP(2, it, 1);
-          // S^T(it+1) = K Q(it+1)^T (overwrites P^T(it): the tensor pipe executes in issue order)
-          if (it + 1 < T) {
+          // S^T(it + kAhead) = K Q(it + kAhead)^T into the buffer P^T(it) was just read from (the tensor pipe executes in
+          // issue order)
+          if (it + kAhead < T) {
             mbar_wait(&bars[kQFull + qsn], qphn);
             tcgen05_fence_after();
-            issue_kmajor(kTmemS, k_kmaj, advance(q_kmaj, qsn * L::kTileBytes));
-            umma_commit(&bars[kSFull]);
+            issue_kmajor(tmem_s, k_kmaj, advance(q_kmaj, qsn * L::kTileBytes));
+            umma_commit(&bars[kSFull + sbuf(it)]);
           }
           FA2_STAMP(2, it, 2);
           // dK += dS^T(it) Q(it)
@@ -366,7 +417,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int r = threadIdx.x & 127;  // key row inside the block == TMEM lane
     const int kv = kv0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = lane_sel + kTmemS + wg * kCmpCols;   // P^T (16-bit) goes over the head of the same columns
+    const uint32_t tS0 = lane_sel + kTmemS + wg * kCmpCols;  // P^T (16-bit) goes over the head of the same columns
     const uint32_t tDP = lane_sel + kTmemDP + wg * kCmpCols;  // ... and dS^T over the head of these
     const float2 neg_c2 = make_float2(-p.scale_log2, -p.scale_log2);
     // spill: this thread's 16-byte pieces of dS^T(m, n) go to [piece = 8 queries][key row][16 B] inside the 32 KB tile,
@@ -424,8 +475,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
       // ---- P^T = exp2(S^T * c - LSE) = exp2(-(LSE - S^T * c)) ----
       if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 0);
+      const uint32_t tS = tS0 + sbuf(it) * 128;
       mbar_wait(&bars[kQFull + qs], qph);  // the LSE row travels with Q
-      mbar_wait(&bars[kSFull], par);
+      mbar_wait(&bars[kSFull + sbuf(it)], spar(it));
       tcgen05_fence_after();
       if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 1);
       uint32_t su[kCmpCols];
@@ -481,9 +533,9 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           pf[j4 * 2] = make_float2(ex2_approx(-tt[0]), ex2_approx(-tt[1]));
           pf[j4 * 2 + 1] = make_float2(ex2_approx(-tt[2]), ex2_approx(-tt[3]));
         } else {
-        if (emulate_pair(j4 * 2)) pf[j4 * 2] = ex2_emul2_neg(t0);
+        if (emulate_pair<D>(j4 * 2)) pf[j4 * 2] = ex2_emul2_neg(t0);
         else pf[j4 * 2] = make_float2(ex2_approx(-t0.x), ex2_approx(-t0.y));
-        if (emulate_pair(j4 * 2 + 1)) pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
+        if (emulate_pair<D>(j4 * 2 + 1)) pf[j4 * 2 + 1] = ex2_emul2_neg(t1);
         else pf[j4 * 2 + 1] = make_float2(ex2_approx(-t1.x), ex2_approx(-t1.y));
         }
       }
@@ -507,7 +559,7 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tmem_wait_st();
       }
       tcgen05_fence_before();
-      mbar_arrive(&bars[kPFull]);
+      mbar_arrive(&bars[kPFull + sbuf(it)]);
       if (r == 0 && (wg == 0 || wg == kCmpWgs - 1)) FA2_STAMP(wg ? 1 : 0, it, 2);
       if (kSpill && it > 0) {
 #pragma unroll
@@ -641,7 +693,7 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
                                      const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
                                      const DkdvParams& p, cudaStream_t stream) {
   auto kernel = fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kExtra>;
-  constexpr int smem = DkdvSmem<D, (kExtra == 1 && D == 128) ? 2 : kQStages, kExtra == 1>::kBytes;
+  constexpr int smem = DkdvSmem<D, q_stages(D, kExtra), kExtra == 1>::kBytes;
   const CUtensorMap& tbias = p.bias_tma ? *p.bias_map : tq;  // placeholder when the bias is read through plain loads
   if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kExtra>>(smem); e != cudaSuccess) return e;
   dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv * (kExtra == 3 ? p.kv_split : 1), p.B);

@@ -35,7 +35,11 @@ def timed(fn):
 t_fwd = timed(lambda: _lib.check(lib.fa2_sm100_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, H, H, S, S, D,
                                                    s3(q), s3(k), s3(v), s3(o), S_pad, scale, int(causal), 17, st), "fwd"))
 out = {"fwd_ms": t_fwd, "fwd_tflops": f_fwd / t_fwd / 1e9}
+import os
+_only = os.environ.get("FA2_KT_MODES")  # e.g. "3,5": time only these backward modes
 for mode, name in ((3, "dkdv"), (4, "dq"), (1, "det"), (5, "spill"), (6, "spill_dkdv"), (7, "spill_dq"), (0, "atomic")):
+    if _only and str(mode) not in _only.split(","):
+        continue
     wsb = lib.fa2_sm100_bwd_workspace_bytes(B, H, S, S, D, int(causal), mode)
     ws = torch.empty(max(wsb, 16), device=dev, dtype=torch.uint8)
     wp = ws.data_ptr() if wsb else None
