@@ -1,7 +1,7 @@
 """clock64() timeline of ONE CTA of the forward kernel (fwd2_sm100.cu) from the trace build of the library:
 
     make -C fa2_triton_b200/csrc TRACE=1
-    FA2_SM100_LIB=fa2_triton_b200/libfa2_sm100_trace.so python scripts/fwd2_trace.py [causal 0|1]
+    FA2_SM100_LIB=fa2_triton_b200/libfa2_sm100_trace.so python scripts/fwd2_trace.py [causal 0|1 [B H S D]]
 
 Per half-block j and tile t: how long the softmax thread waited for S (`wait`), its busy time split into load / max /
 exp / store, and the round trip R(j) = [S(j+2) seen by the softmax thread] - [P(j) handed over]; for the issuer of the
@@ -23,7 +23,7 @@ from fa2_triton_b200 import _lib  # noqa: E402
 causal = bool(int(sys.argv[1])) if len(sys.argv) > 1 else False
 lib = _lib.load()
 dev = "cuda:0"
-B, H, S, D = 4, 32, 4096, 128
+B, H, S, D = (int(x) for x in sys.argv[2:6]) if len(sys.argv) > 5 else (4, 32, 4096, 128)
 g = torch.Generator(device=dev).manual_seed(0)
 q, k, v = (torch.empty(B, S, H, D, device=dev).normal_(0, 0.5, generator=g).bfloat16() for _ in range(3))
 for _ in range(3):
