@@ -37,7 +37,13 @@ WORKLOADS = {
     "cfg4": dict(B=2, H=16, S=16384, D=64, causal=False, bwd=True, scaling="weak"),
     "cfg5": dict(B=32, H=32, S=8192, D=128, causal=True, bwd=True, scaling="strong"),
 }
-METRIC = "fwd+bwd TFLOP/s (bf16, causal, S=4096, D=128)"
+METRIC = "fwd+bwd TFLOP/s (bf16, causal, S=4096, D=128)"  # BASELINE.json's metric: the default workload (cfg3)
+
+
+def metric_name(w):
+    """The metric label of a workload: BASELINE.json's for cfg3, the same wording with the workload's own shape otherwise."""
+    return (f"{'fwd+bwd' if w['bwd'] else 'fwd'} TFLOP/s (bf16, {'causal' if w['causal'] else 'non-causal'}, "
+            f"S={w['S']}, D={w['D']})")
 
 
 def fa_flops(B, H, Sq, Sk, D, causal, bwd):
@@ -179,7 +185,7 @@ def run_reference_arm(args):
     w = WORKLOADS[args.workload]
     cb, dt = cpu_baseline_run(torch, w, args.steps, args.warmup, budget_s=120.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(w), "value": cb["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, w), "timed_sample": cb["sample"]},
@@ -470,7 +476,7 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(w), "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, w), "per_gpu_batch": B_local, "global_batch": B_global,

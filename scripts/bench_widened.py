@@ -37,6 +37,11 @@ CASES = [
     ("bias [B, H, Sq, Sk] bf16", 2, 2048, 2048, 16, 16, 128, torch.bfloat16, False, True, {"bias": (2, 16)}),
     ("dropout p=0.1, forward only", 4, 4096, 4096, 32, 32, 128, torch.bfloat16, True, False, {"dropout_p": 0.1}),
     ("forward only (cfg2)", 4, 4096, 4096, 32, 32, 128, torch.bfloat16, True, False, {}),
+    ("head dim 256, causal", 4, 4096, 4096, 16, 16, 256, torch.bfloat16, True, True, {}),
+    ("head dim 207 (zero-padded to 208), causal", 4, 4096, 4096, 16, 16, 207, torch.bfloat16, True, True, {}),
+    ("head dim 256, forward only", 4, 4096, 4096, 16, 16, 256, torch.bfloat16, True, False, {}),
+    ("cfg4: S=16384, head dim 64, non-causal", 2, 16384, 16384, 16, 16, 64, torch.bfloat16, False, True, {}),
+    ("cfg4 ragged tail: S=1000, head dim 64, non-causal", 2, 1000, 1000, 16, 16, 64, torch.bfloat16, False, True, {}),
 ]
 
 for name, B, Sq, Sk, Hq, Hkv, D, dtype, causal, bwd, extra in CASES:
