@@ -43,7 +43,7 @@ SIGNATURES = {
                       + [_c_int64, _c_float, _c_int, _c_int, _c_void_p]),
     "fa2_sm100_fwd_ext": (_c_int, [_c_void_p] * 5 + [_c_int] * 6 + [ctypes.POINTER(_c_int64)] * 4
                           + [_c_int64, _c_float, _c_int, _c_int]
-                          + [_c_void_p, _c_int, ctypes.POINTER(_c_int64), _c_float, ctypes.c_uint64, _c_void_p]),
+                          + [_c_void_p, _c_int, ctypes.POINTER(_c_int64), _c_float, ctypes.c_uint64, ctypes.c_uint32, _c_void_p]),
     "fa2_sm100_varlen_workspace_bytes": (_c_size_t, [_c_int]),
     "fa2_sm100_fwd_varlen": (_c_int, [_c_void_p] * 5 + [_c_int] * 5 + [ctypes.POINTER(_c_int64)] * 4
                              + [_c_int64, _c_float, _c_int, _c_int] + [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),

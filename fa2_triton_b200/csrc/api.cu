@@ -190,7 +190,8 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
              int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
              const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
              const void* bias, int bias_dtype, const int64_t bias_strides[3], float dropout_p,
-             uint64_t dropout_seed, const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes, void* stream);
+             uint64_t dropout_seed, uint32_t dropout_offset, const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes,
+             void* stream);
 int bwd_impl(const void* dout, const void* q, const void* k, const void* v, const float* lse,
              const float* delta, void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, int B,
              int Hq, int Hkv, int Sq, int Sk, int D, const int64_t do_strides[3], const int64_t q_strides[3],
@@ -220,17 +221,17 @@ int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
                   void* stream) {
   return fa2_sm100_fwd_ext(q, k, v, o, lse, B, Hq, Hkv, Sq, Sk, D, q_strides, k_strides, v_strides, o_strides,
-                           lse_row_stride, softmax_scale, causal, dtype, nullptr, 0, nullptr, 0.f, 0ull, stream);
+                           lse_row_stride, softmax_scale, causal, dtype, nullptr, 0, nullptr, 0.f, 0ull, 0u, stream);
 }
 
 int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int Sq,
                       int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
                       const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
                       const void* bias, int bias_dtype, const int64_t bias_strides[3], float dropout_p,
-                      uint64_t dropout_seed, void* stream) {
+                      uint64_t dropout_seed, uint32_t dropout_offset, void* stream) {
   return fwd_impl(q, k, v, o, lse, B, Hq, Hkv, Sq, Sk, D, q_strides, k_strides, v_strides, o_strides, lse_row_stride,
-                  softmax_scale, causal, dtype, bias, bias_dtype, bias_strides, dropout_p, dropout_seed, nullptr, nullptr,
-                  0, stream);
+                  softmax_scale, causal, dtype, bias, bias_dtype, bias_strides, dropout_p, dropout_seed, dropout_offset,
+                  nullptr, nullptr, 0, stream);
 }
 
 int fa2_sm100_fwd_varlen(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int S,
@@ -239,7 +240,7 @@ int fa2_sm100_fwd_varlen(const void* q, const void* k, const void* v, void* o, f
                          const int32_t* seqlens, void* tmap_workspace, size_t tmap_workspace_bytes, void* stream) {
   if (!seqlens) return fail(FA2_E_NULL_POINTER, "seqlens: null pointer");
   return fwd_impl(q, k, v, o, lse, B, Hq, Hkv, S, S, D, q_strides, k_strides, v_strides, o_strides, lse_row_stride,
-                  softmax_scale, causal, dtype, nullptr, 0, nullptr, 0.f, 0ull, seqlens, tmap_workspace,
+                  softmax_scale, causal, dtype, nullptr, 0, nullptr, 0.f, 0ull, 0u, seqlens, tmap_workspace,
                   tmap_workspace_bytes, stream);
 }
 
@@ -251,7 +252,8 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
              int Sk, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
              const int64_t o_strides[3], int64_t lse_row_stride, float softmax_scale, int causal, int dtype,
              const void* bias, int bias_dtype, const int64_t bias_strides[3], float dropout_p,
-             uint64_t dropout_seed, const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes, void* stream) {
+             uint64_t dropout_seed, uint32_t dropout_offset, const int32_t* seqlens, void* tmap_ws, size_t tmap_ws_bytes,
+             void* stream) {
   if (int e = check_common(B, Hq, Hkv, Sq, Sk, D, dtype)) return e;
   if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(FA2_E_BAD_SHAPE, "dropout_p must be in [0, 1)");
   if (!lse) return fail(FA2_E_NULL_POINTER, "lse: null pointer");
@@ -298,6 +300,7 @@ int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, i
   p.inv_keep = 1.0f / (1.0f - dropout_p);
   p.seed_lo = static_cast<uint32_t>(dropout_seed & 0xffffffffull);
   p.seed_hi = static_cast<uint32_t>(dropout_seed >> 32);
+  p.drop_offset = dropout_offset;
   if (seqlens) {
     const VarlenTensor vt[4] = {{&tq, q, q_strides[0]}, {&tk, k, k_strides[0]}, {&tv, v, v_strides[0]}, {&to, o, o_strides[0]}};
     if (int e = setup_varlen_maps(vt, 4, seqlens, tmap_ws, tmap_ws_bytes, B, Sq, static_cast<cudaStream_t>(stream))) return e;

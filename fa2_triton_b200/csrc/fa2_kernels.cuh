@@ -91,6 +91,7 @@ struct FwdParams {
   float dropout_p;      // 0: no dropout
   float inv_keep;       // 1 / (1 - dropout_p)
   uint32_t seed_lo, seed_hi;
+  uint32_t drop_offset;  // added to every dropout counter (modulo 2^32); 0 for a whole [B, Hq, Sq, Sk] call
   const int* seqlens;         // variable-length mode (see above), else nullptr
   const CUtensorMap* vmaps;
   // head dims below the kernel's: the zero columns TMA fills in need no products. d_steps = ceil(d / 16) k-steps of

@@ -297,8 +297,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     float m_ref = -INFINITY;
     float l = 0.f;
     // linear index of this row's first score in a [B, Hq, Sq, Sk] tensor, modulo 2^32: the dropout counter
-    // (src/forward/kernel.py:147-149)
-    const uint32_t drop_row_off =
+    // (src/forward/kernel.py:147-149); drop_offset is what the caller adds for a sequence of a packed batch
+    const uint32_t drop_row_off = p.drop_offset +
         ((static_cast<uint32_t>(batch) * p.Hq + head) * static_cast<uint32_t>(p.Sq) + static_cast<uint32_t>(row)) *
         static_cast<uint32_t>(p.Sk);
     (void)drop_row_off;

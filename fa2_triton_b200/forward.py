@@ -136,9 +136,11 @@ def _flash_attn_forward(
     softmax_scale: Optional[float] = None,
     dropout_seed: Optional[int] = None,
     out: Optional[Tensor] = None,
+    dropout_offset: int = 0,
 ) -> Tuple[Tensor, Tensor, float, int]:
     """Returns ``(o, lse, softmax_scale, dropout_seed)`` like src/forward/caller.py:122.
     ``out`` (extension): write O into this tensor (any strides with a contiguous last dimension).
+    ``dropout_offset`` (extension): added to every dropout counter modulo 2**32 (a sequence of a packed batch).
 
     ``lse`` is fp32 ``[B, Hq, ceil(Sq/128)*128]`` in the log2 domain (src/forward/caller.py:73-74,
     src/forward/kernel.py:119); entries past ``Sq`` are 0.
@@ -150,10 +152,9 @@ def _flash_attn_forward(
         q, k, v = kernel_addressable(q), kernel_addressable(k), kernel_addressable(v)
     if attention_mask is not None:
         assert bias is None, "Attention mask is not supported along with attention bias. Just use bias instead."
-        if dropout_p and dropout_p > 0:
-            # the reference numbers its dropout counters over the packed batch (src/forward/kernel.py:147-149); the
-            # per-sequence views used here would draw a different mask
-            raise NotImplementedError("dropout together with attention_mask is not supported")
+        with_dropout = bool(dropout_p and dropout_p > 0)
+        if with_dropout:
+            dropout_seed = handle_dropout(dropout_p, dropout_seed, is_forward=True)
         # Variable-length mode (src/forward/caller.py:25-59): every sequence attends within its own unpadded prefix and
         # padded rows of O are zero. Instead of the reference's pack / unpack copies each sequence is a strided view
         # handed to the kernel (TMA takes the strides); O is written in place.
@@ -163,7 +164,7 @@ def _flash_attn_forward(
         o = torch.zeros_like(q)
         seqlen_q_rounded = math.ceil(seqlen_q / 128) * 128
         lse = torch.zeros((batch, nheads_q, seqlen_q_rounded), device=q.device, dtype=torch.float32)
-        if varlen_in_kernel(q, k, v):
+        if varlen_in_kernel(q, k, v) and not with_dropout:
             # One launch over the whole padded batch: the lengths stay on the device (no .item() / .tolist() sync) and a
             # setup kernel derives per-sequence tensor maps from them (include/fa2_sm100.h, fa2_sm100_fwd_varlen).
             assert nheads_q % nheads_kv == 0, f"{nheads_q = } is not divisible by {nheads_kv =}"
@@ -182,18 +183,25 @@ def _flash_attn_forward(
                     seqlens.data_ptr(), tmap_ws.data_ptr(), tmap_ws.numel(), _stream_ptr(q.device))
             _lib.check(code, "fa2_sm100_fwd_varlen")
             return o, lse, scale, 0 if dropout_seed is None else dropout_seed
+        # One launch per sequence over views (odd head dims; dropout). With dropout the reference numbers the counters of
+        # a sequence of length L that starts at row c of the PACKED batch as L * (c + L * head) + row * L + col
+        # (src/forward/kernel.py:105-112, 147-149: off_batch is 0 in its VARLEN mode): a [1, L, H, D] call whose counters
+        # start at L * c draws exactly that mask. The lengths are read on the host here, like src/utils.py:14 does.
+        start = 0
         for b, n in enumerate(sequence_lengths(attention_mask)):
             if n == 0:
                 continue
-            ob, lb, _, _ = _flash_attn_forward(q[b:b + 1, :n], k[b:b + 1, :n], v[b:b + 1, :n], None, None, 0.0, causal,
-                                               scale, dropout_seed, out=o[b:b + 1, :n])
+            ob, lb, _, _ = _flash_attn_forward(q[b:b + 1, :n], k[b:b + 1, :n], v[b:b + 1, :n], None, None,
+                                               dropout_p if with_dropout else 0.0, causal, scale, dropout_seed,
+                                               out=o[b:b + 1, :n], dropout_offset=(n * start) & 0xffffffff)
             lse[b, :, :lb.shape[-1]] = lb[0]
+            start += n
         return o, lse, scale, 0 if dropout_seed is None else dropout_seed
     if not runs_natively(head_dim):
         d = padded_head_dim(head_dim)
         scale = 1.0 / math.sqrt(head_dim) if softmax_scale is None else float(softmax_scale)
         o, lse, _, seed = _flash_attn_forward(pad_last(q, d), pad_last(k, d), pad_last(v, d), None, bias, dropout_p,
-                                              causal, scale, dropout_seed)
+                                              causal, scale, dropout_seed, dropout_offset=dropout_offset)
         o = o[..., :head_dim]
         if out is not None:
             out.copy_(o)
@@ -226,6 +234,6 @@ def _flash_attn_forward(
             code = lib.fa2_sm100_fwd(*args, _stream_ptr(q.device))
         else:
             code = lib.fa2_sm100_fwd_ext(*args, *_lib.bias_args(bias), float(dropout_p), int(dropout_seed),
-                                         _stream_ptr(q.device))
+                                         int(dropout_offset) & 0xffffffff, _stream_ptr(q.device))
     _lib.check(code, "fa2_sm100_fwd")
     return o, lse, softmax_scale, dropout_seed

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 11
+#define FA2_SM100_ABI_VERSION 12
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17
@@ -97,6 +97,10 @@ int fa2_sm100_fwd(const void* q, const void* k, const void* v, void* o, float* l
  *                 - Triton's Philox-4x32-10 stream, bit-identical to the reference's mask (src/forward/
  *                 compute_row_blocks.py:76-79, tests/utils.py:169-207) - after the row sum was taken, and O is scaled by
  *                 1 / (1 - p) (src/forward/kernel.py:256-257). The LSE is that of the undropped row. 0: no dropout.
+ *   dropout_offset  added to every counter, modulo 2^32 (ABI v12). 0 for a whole batch. With `attention_mask` the reference
+ *                 numbers the counters of a sequence of length L that starts at row c of the PACKED batch as
+ *                 L * (c + L * head) + row * L + col (src/forward/kernel.py:105-112, 147-149): a call on that sequence's
+ *                 [1, L, H, D] views with dropout_offset = L * c draws exactly that mask.
  * The reference has no dropout in its backward (src/utils.py:87-88: NotImplementedError); neither has this library. */
 int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, float* lse,
                       int B, int Hq, int Hkv, int Sq, int Sk, int D,
@@ -104,7 +108,7 @@ int fa2_sm100_fwd_ext(const void* q, const void* k, const void* v, void* o, floa
                       const int64_t o_strides[3], int64_t lse_row_stride,
                       float softmax_scale, int causal, int dtype,
                       const void* bias, int bias_dtype, const int64_t bias_strides[3],
-                      float dropout_p, uint64_t dropout_seed, void* stream);
+                      float dropout_p, uint64_t dropout_seed, uint32_t dropout_offset, void* stream);
 
 /* delta[b, h, i] = sum_d O[b, i, h, d] * dO[b, i, h, d] in fp32; rows in [Sq, lse_row_stride) are set to 0.
  * If `workspace` is not NULL the same launch also zero-fills it (the reference zero-allocates dq at

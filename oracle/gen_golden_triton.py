@@ -95,6 +95,12 @@ CASES = {
     "triton_bias_causal_fp16_b1h3sq127sk130d32": (1, 127, 130, 3, 3, 32, True, {"bias": True}),
     "triton_dropout_fwd_fp16_b2h3sq128sk217d64": (2, 128, 217, 3, 3, 64, False, {"dropout_p": 0.1, "seed": 20261018}),
     "triton_dropout_causal_fwd_fp16_b1h2sq100sk100d64": (1, 100, 100, 2, 2, 64, True, {"dropout_p": 0.17, "seed": 7}),
+    # dropout together with attention_mask: the counters are numbered over the PACKED batch (src/forward/kernel.py:105-112,
+    # 147-149). The reference's test helper cannot build this mask (it numbers [B, H, Sq, Sk]), so only O and the LSE are kept.
+    "triton_varlen_dropout_fwd_fp16_b3h2s96d64": (3, 96, 96, 2, 2, 64, False,
+                                                   {"lengths": (96, 57, 20), "dropout_p": 0.2, "seed": 424242}),
+    "triton_varlen_dropout_causal_fwd_fp16_b3h2s80d64": (3, 80, 80, 2, 2, 64, True,
+                                                          {"lengths": (33, 80, 64), "dropout_p": 0.1, "seed": 99}),
 }
 
 
@@ -140,7 +146,9 @@ def main():
             saved["attention_mask"] = mask.numpy()
         if bias is not None:
             saved["bias"] = bias.numpy()
-        if dropout_p > 0:
+        if dropout_p > 0 and mask is not None:
+            saved.update(dropout_p=np.array(dropout_p), dropout_seed=np.array(seed_used, dtype=np.int64))
+        elif dropout_p > 0:
             # the keep-mask exactly as the reference's tests build it (tests/utils.py:169-207)
             keep = torch.zeros(B, Hq, Sq, Sk)
             n = keep.numel()

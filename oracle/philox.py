@@ -43,3 +43,21 @@ def dropout_keep_mask(seed: int, dropout_p: float, B: int, H: int, Sq: int, Sk: 
     """bool [B, H, Sq, Sk], True where the probability is kept."""
     offs = np.arange(B * H * Sq * Sk, dtype=np.uint64).reshape(B, H, Sq, Sk)
     return uniform(seed, offs) > np.float32(dropout_p)
+
+
+def dropout_keep_mask_varlen(seed: int, dropout_p: float, lengths, H: int, S: int) -> np.ndarray:
+    """bool [B, H, S, S] keep-mask of a right-padded batch given through `attention_mask` (the reference's VARLEN mode):
+    sequence b of length L that starts at row c of the PACKED batch draws tl.rand at offset
+    L * (c + L * head) + row * L + col  (src/forward/kernel.py:105-112: `off_batch = 0`, `cu_seq_start_q`;
+    :147-149: `dropout_off`), int32 arithmetic, i.e. modulo 2**32. Entries outside a sequence are True (unused)."""
+    keep = np.ones((len(lengths), H, S, S), dtype=bool)
+    start = 0
+    for b, L in enumerate(int(n) for n in lengths):
+        if L > 0:
+            head = np.arange(H, dtype=np.uint64)[:, None, None]
+            row = np.arange(L, dtype=np.uint64)[None, :, None]
+            col = np.arange(L, dtype=np.uint64)[None, None, :]
+            offs = (np.uint64(L) * (np.uint64(start) + np.uint64(L) * head) + row * np.uint64(L) + col) & np.uint64(0xFFFFFFFF)
+            keep[b, :, :L, :L] = uniform(seed, offs) > np.float32(dropout_p)
+        start += L
+    return keep

@@ -70,6 +70,12 @@ def triton_golden_extras(g):
     if "dropout_keep" in g:
         keep = np.unpackbits(g["dropout_keep"])[: B * H * Sq * Sk].astype(bool).reshape(B, H, Sq, Sk)
         p = float(g["dropout_p"])
+    elif "dropout_p" in g:
+        # dropout together with attention_mask: no stored mask (the reference's helper cannot build it); the restated
+        # packed-batch numbering (oracle/philox.py) is checked through O, which the Triton kernel produced
+        from oracle import philox
+        p = float(g["dropout_p"])
+        keep = philox.dropout_keep_mask_varlen(int(g["dropout_seed"]), p, seqlens, H, Sq)
     return seqlens, bias, keep, p
 
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/fa2_sm100.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.fa2_sm100_version() == 11
+    assert lib.fa2_sm100_version() == 12
 
 
 def test_workspace_size_formula():
@@ -81,9 +81,10 @@ def test_python_surface_matches_reference_signatures():
     assert list(inspect.signature(pkg.flash_attn_func).parameters) == want  # src/wrapper.py:89-99
     assert list(inspect.signature(pkg.FlashAttnFunc.forward).parameters) == ["ctx"] + want  # src/wrapper.py:13-24
     fwd = list(inspect.signature(pkg._flash_attn_forward).parameters)
-    # the reference's nine parameters in its order (src/forward/caller.py:12-22); `out` is a trailing extension
+    # the reference's nine parameters in its order (src/forward/caller.py:12-22); `out` and `dropout_offset` are trailing
+    # extensions
     assert fwd[:9] == ["q", "k", "v", "attention_mask", "bias", "dropout_p", "causal", "softmax_scale", "dropout_seed"]
-    assert fwd[9:] == ["out"]
+    assert fwd[9:] == ["out", "dropout_offset"]
     bwd = list(inspect.signature(pkg._flash_attn_backward).parameters)
     assert bwd[:12] == ["dO", "q", "k", "v", "bias", "attention_mask", "o", "lse", "dropout_p", "causal",
                         "softmax_scale", "dropout_seed"]  # src/backward/caller.py:14-27

@@ -200,6 +200,29 @@ def test_dropout_large_seed_bias_and_repeatability():
     assert 0 <= drawn < 2**32 and torch.isfinite(o4).all()
 
 
+@pytest.mark.parametrize("D", [64, 128, 59])
+@pytest.mark.parametrize("causal", [False, True])
+def test_dropout_with_attention_mask_numbers_its_counters_over_the_packed_batch(D, causal):
+    """dropout together with attention_mask: the reference's VARLEN mode draws tl.rand at
+    L * (start + L * head) + row * L + col for a sequence of length L starting at row `start` of the packed batch
+    (src/forward/kernel.py:105-112, 147-149; pinned by tests/golden/triton_varlen_dropout_*.npz). The oracle gets that
+    mask (oracle/philox.py); padded rows of O are zero; same seed -> same bits."""
+    B, S, H = 4, 200, 3
+    lengths = (200, 131, 1, 64)
+    q, k, v, _ = generate_test_data(B, S, S, H, H, D, torch.float16, DEV, 5)
+    mask = torch.zeros(B, S, dtype=torch.bool, device=DEV)
+    for b, n in enumerate(lengths):
+        mask[b, :n] = True
+    p, seed = 0.15, 2026
+    o1 = fa2.flash_attn_func(q, k, v, attention_mask=mask, causal=causal, dropout_p=p, dropout_seed=seed)
+    o2 = fa2.flash_attn_func(q, k, v, attention_mask=mask, causal=causal, dropout_p=p, dropout_seed=seed)
+    assert torch.equal(o1, o2)
+    keep = torch.from_numpy(philox.dropout_keep_mask_varlen(seed, p, lengths, H, S)).to(DEV)
+    ref = er.flash_attn_reference(q, k, v, causal=causal, padding_mask=mask, dropout_p=p, dropout_mask=keep)
+    assert_close_16("O", o1, ref)
+    assert float(o1[~mask].abs().max()) == 0.0
+
+
 def test_dropout_backward_is_not_implemented_like_the_reference():
     q, k, v, do = generate_test_data(1, 128, 128, 2, 2, 64, torch.bfloat16, DEV)
     qq = q.clone().requires_grad_(True)

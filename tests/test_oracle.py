@@ -153,7 +153,7 @@ def test_eager_port_matches_triton_kernel(name):
         np.testing.assert_allclose(got.float().numpy(), g[key].astype(np.float32), rtol=1e-2, atol=atol)
 
 
-@pytest.mark.parametrize("name", triton_golden_names(with_backward=False))
+@pytest.mark.parametrize("name", [n for n in triton_golden_names(with_backward=False) if "varlen" not in n])
 def test_philox_restatement_is_bit_exact(name):
     """tl.rand(seed, linear offset) > p, as drawn by the reference (tests/utils.py:169-207): every bit of the mask."""
     g = load_golden(name)
