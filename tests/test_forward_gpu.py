@@ -55,6 +55,36 @@ def test_forward_head_dims_above_128(Sq, Sk, D, causal, dtype):
     run_case(2, Sq, Sk, 4, 2, D, causal, dtype, seed=D)
 
 
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [64, 128, 256])
+def test_forward_reference_maximum_moves_in_late_blocks(D, causal):
+    """The reference maximum of a row only moves when a block exceeds it by 2^8 (lazy rescale), which random N(0, 0.5)
+    inputs never do after the first block. Keys whose magnitude grows along the sequence make later blocks exceed the running
+    maximum by far more than that, again and again: the O accumulator is rescaled in mid-row, and at head dim 64 the
+    exponentials formed ahead of the block maximum are thrown away and redone (fwd2_sm100.cu). O and the LSE against the
+    oracle, and run-to-run identical."""
+    B, S, H = 2, 1024, 3
+    q, k, v, _ = generate_test_data(B, S, S, H, H, D, torch.bfloat16, DEV, 11)
+    ramp = torch.linspace(0.2, 6.0, S, device=DEV).view(1, S, 1, 1)
+    k = (k.float() * ramp).to(torch.bfloat16)       # |scores| grow ~30x from the first to the last key
+    q = (q.float() * 2.0).to(torch.bfloat16)
+    o, lse, _, _ = fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
+    o2, lse2, _, _ = fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
+    assert torch.equal(o, o2) and torch.equal(lse, lse2)
+    ref = er.flash_attn_reference(q, k, v, causal=causal, upcast=True)
+    assert_close_16("O", o, ref)
+    lse_ref = er.lse_log2(q, k, causal=causal)
+    # the scores reach a few hundred in the log2 domain: compare the LSE relative to its size (fp32 has 24 bits)
+    err = (lse[:, :, :S] - lse_ref).abs()
+    assert (err <= ATOL_LSE + 2e-6 * lse_ref.abs()).all(), float(err.max())
+    # the premise of the test: in most rows the maximum over the last quarter of the keys exceeds the maximum over the first
+    # quarter by more than 2^8 in the log2 domain
+    sc = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * (1.4426950408889634 / math.sqrt(D))
+    if not causal:
+        grows = (sc[..., 3 * S // 4:].amax(-1) - sc[..., : S // 4].amax(-1)) > 8.0
+        assert grows.float().mean().item() > 0.5
+
+
 def test_forward_long_rows_many_half_blocks():
     """Enough 64-key half-blocks for every ring / barrier phase of fwd2_sm100.cu to wrap several times, ragged ends,
     both tiles of a CTA with different block counts (causal) and Sq != Sk."""
