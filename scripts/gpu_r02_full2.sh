@@ -18,7 +18,7 @@ for f in ("bench", "bench_cfg2", "bench_cfg4"):
         print("  sustained", {k: round(d["sustained"][k], 4) for k in ("value", "ms_per_step")}, d["sustained"]["clocks"]["sm_mhz"], d["sustained"]["clocks"]["reasons"])
         print("  kernels", {k[:26]: round(v["ms"], 4) for k, v in d["roofline"]["kernels"].items()}, "sum", round(d["roofline"]["sum_of_kernels_ms"], 4))
         print("  clocks", d["clocks"])
-        if "triton_baseline" in d: print("  triton", d["triton_baseline"].get("value"), d["triton_baseline"].get("speedup_ours_over_triton"))
+        if d.get("triton_baseline"): print("  triton", d["triton_baseline"].get("value"), d["triton_baseline"].get("speedup_ours_over_triton"))
         if "e2e" in d and d["e2e"]: print("  e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"])
     except Exception as e:
         print(f, "parse failed", e)
