@@ -182,20 +182,6 @@ int make_bias_view(fa2::BiasView* view, const void* bias, int bias_dtype, const 
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// counters of the pipelined backward behind the dS tiles of the spilled-dS workspace (fa2_kernels.cuh: PipeParams)
-size_t spill_counter_bytes(int B, int Hq, int Sq) {
-  return (fa2::pipe_counter_ints(B, Hq, Sq) * sizeof(int) + 1023) / 1024 * 1024;
-}
-
-// Pipelined backward (bwd_pipe_sm100.cu) for mode 5 at head dims 65..128 without bias / variable lengths / split head
-// groups: opt-in with FA2_SM100_PIPE=1 (=2: without discarding the consumed tiles from L2). Bit-identical to the two
-// kernels run one after the other, which stay the default: measured at parity with them at best (profiles/
-// r02_experiments.txt, item 9).
-int pipe_mode() {
-  static const int n = [] { const char* e = getenv("FA2_SM100_PIPE"); return e ? atoi(e) : 0; }();
-  return n;
-}
-
 // The kernels are instantiated for head dims 64, 128 and 256. Any multiple of 8 below runs in the next instantiation: the
 // tensor maps carry the real head dim, so TMA zero-fills the missing columns on load and clips them on store.
 int kernel_head_dim(int D) { return D <= 64 ? 64 : D <= 128 ? 128 : 256; }
@@ -398,11 +384,10 @@ size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int c
   if (deterministic == FA2_DQ_NONE || deterministic == FA2_DQ_DETERMINISTIC || deterministic == FA2_DQ_ONLY)
     return 256;  // no accumulator, only the work-item counters of the persistent kernels' schedulers
   if (deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ) {
-    // header (1 KB) + one 32 KB dS tile per visible (query block, key block) pair + the counters of the pipelined backward
-    // (two cursors, then per (batch, head) one cursor and one word per query block; rounded up to 1 KB)
+    // scheduler counter (padded to 1 KB) + one 32 KB dS tile per visible (query block, key block) pair
     if (Sk < 1) return 0;
     const long long tiles = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);
-    return 1024 + static_cast<size_t>(B) * Hq * static_cast<size_t>(tiles) * fa2::kDsTileBytes + spill_counter_bytes(B, Hq, Sq);
+    return 1024 + static_cast<size_t>(B) * Hq * static_cast<size_t>(tiles) * fa2::kDsTileBytes;
   }
   const size_t sq_pad = static_cast<size_t>(round_up(Sq, 128));
   const size_t accum = static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float);
@@ -661,39 +646,6 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
       part_dk_used = k.part_dk;
       k.d_steps = (D + 15) / 16;
       k.d_cols = round_up(D, 16);
-      if (deterministic == FA2_DQ_DET_SPILL && Dk == 128 && !seqlens && !bias && kv_split == 1 && pipe_mode() > 0) {
-        // Pipelined backward: dK, dV and dQ in one persistent kernel, dS tiles handed over through L2 (bwd_pipe_sm100.cu)
-        int* ctr = reinterpret_cast<int*>(static_cast<char*>(workspace) + need - spill_counter_bytes(B, Hq, Sq));
-        ce = cudaMemsetAsync(ctr, 0, fa2::pipe_counter_ints(B, Hq, Sq) * sizeof(int), st);
-        if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd counter memset");
-        fa2::PipeParams pp{};
-        pp.dkdv_next = ctr;
-        pp.lo_hint = ctr + 1;
-        pp.next_row = ctr + 32;
-        pp.done = ctr + 32 + static_cast<size_t>(B) * Hq;
-        pp.n_heads = B * Hq;
-        pp.n_q_blocks = (Sq + 127) / 128;
-        pp.n_k_blocks = (Sk + 127) / 128;
-        pp.n_dkdv = pp.n_k_blocks * Hkv * B;
-        pp.discard = pipe_mode() == 1 ? 1 : 0;
-        pp.rows_per_claim = [] { const char* e = getenv("FA2_SM100_PIPE_G"); const int g = e ? atoi(e) : 4; return g < 1 ? 1 : g; }();
-        k.zero_word = nullptr;
-        k.done = pp.done;
-        fa2::DqSpillParams d{};
-        d.ds_spill = spill_base;
-        d.tiles_per_head = tiles_per_head;
-        d.sched = nullptr;
-        d.dq = dq;
-        for (int i = 0; i < 3; ++i) d.dq_strides[i] = dq_strides[i];
-        d.dq_is_16bit = dq_dtype == dtype ? 1 : 0;
-        d.B = B; d.Hq = Hq; d.Hkv = Hkv; d.Sq = Sq; d.Sk = Sk;
-        d.softmax_scale = softmax_scale;
-        d.causal = causal ? 1 : 0;
-        d.d_actual = D;
-        ce = fa2::launch_bwd_pipe(Dk, dtype == FA2_DTYPE_BF16, tq, tk, tv, tdo, tdk, tdv, k, d, pp, st);
-        if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd pipelined launch");
-        return 0;
-      }
       ce = fa2::launch_bwd_dkdv(Dk, dtype == FA2_DTYPE_BF16, spill, tq, tk, tv, tdo, tdk, tdv, k, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "fa2_sm100_bwd launch");

@@ -200,9 +200,6 @@ struct DkdvParams {
   float scale_log2;
   int causal;
   int* zero_word;         // work-item counter of the dQ kernel that follows on the stream: cleared by CTA (0, 0, 0), or nullptr
-  // Pipelined backward (bwd_pipe_sm100.cu): done[(batch * Hq + head) * n_q_blocks + m] counts the dS tiles of query block
-  // m that have reached global memory (one atomicAdd per tile, after its bulk store has completed). nullptr otherwise.
-  int* done;
   BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
   // kBias: a 16-bit bias whose rows TMA can address (16-byte aligned base and strides) is staged tile by tile through
   // shared memory with `bias_map` ((Sk, Sq, 1 | Hq, 1 | B), box 64 x 128); otherwise every thread loads its values itself
@@ -250,31 +247,6 @@ struct DqSpillParams {
   const CUtensorMap* vmaps;
 };
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream);
-
-// Pipelined deterministic backward (bwd_pipe_sm100.cu): ONE persistent kernel whose CTAs switch between dK/dV items
-// (key block, kv head, batch - the body of the dK/dV kernel, dS tiles spilled) and dQ items (query block, head, batch -
-// the body of the dQ kernel), a dQ item being taken up as soon as all of its tiles have been written, while they are
-// still in L2. Same arithmetic and summation order as the two kernels run one after the other: bit-identical results.
-// Counters (device memory, all zero on entry):
-struct PipeParams {
-  int* dkdv_next;  // dK/dV items handed out so far
-  int* lo_hint;    // every (batch, head) below this index has all its dQ items claimed
-  int* next_row;   // [B * Hq] next unclaimed GROUP of query blocks of the head (claimed in ascending order, only when ready)
-  int* done;       // [B * Hq][n_q_blocks] dS tiles of the query block that have reached global memory
-  int n_heads;     // B * Hq
-  int n_q_blocks;
-  int n_k_blocks;
-  int n_dkdv;      // n_k_blocks * Hkv * B
-  int rows_per_claim;  // query blocks per claimed group (>= 1)
-  int discard;     // 1: drop a tile's lines from L2 once it sits in shared memory (they never travel to HBM)
-};
-// counters of the pipelined backward, in ints: [dkdv_next, lo_hint, pad to 32][next_row: B * Hq][done: B * Hq * n_q_blocks]
-inline size_t pipe_counter_ints(int B, int Hq, int Sq) {
-  return 32 + static_cast<size_t>(B) * Hq * (1 + static_cast<size_t>((Sq + 127) / 128));
-}
-cudaError_t launch_bwd_pipe(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                            const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv, const DkdvParams& k,
-                            const DqSpillParams& d, const PipeParams& pp, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // deterministic backward for head dims 129..256 (bwd256_sm100.cu)

@@ -6,7 +6,7 @@
 set -e
 cd "$(dirname "$0")/../fa2_triton_b200/csrc"
 mkdir -p ../../variants
-ALL="api fwd_sm100 fwd2_sm100 bwd_sm100 bwd_dkdv_sm100 bwd_dq_sm100 bwd_dq_spill_sm100 bwd_pipe_sm100 bwd256_sm100 varlen_sm100"
+ALL="api fwd_sm100 fwd2_sm100 bwd_sm100 bwd_dkdv_sm100 bwd_dq_sm100 bwd_dq_spill_sm100 bwd256_sm100 varlen_sm100"
 while [ $# -gt 2 ]; do
   name=$1; files=$2; flags=$3; shift 3
   d=../../variants/obj_$name; mkdir -p $d

@@ -309,43 +309,3 @@ def test_backward_head_dim_256_modes_and_repeatability():
     assert dq is None and torch.equal(dk, base[1]) and torch.equal(dv, base[2])
     dq, dk, dv = fa2._flash_attn_backward(do, q, k, v, None, None, o, lse, 0.0, True, scale, seed, need_dkdv=False)
     assert dk is None and dv is None and torch.equal(dq, base[0])
-
-
-@pytest.mark.parametrize("shape", [(2, 16, 16, 2048, 2048, 128, True), (1, 8, 2, 1000, 1500, 128, True),
-                                   (3, 6, 6, 640, 640, 64, False), (1, 40, 40, 1024, 1024, 128, True),
-                                   (2, 4, 4, 384, 129, 128, True), (2, 8, 8, 1536, 1536, 128, False),
-                                   (1, 12, 4, 1500, 700, 96, True), (4, 32, 32, 4096, 4096, 128, True)])
-def test_pipelined_backward_equals_the_two_kernels_run_in_sequence(shape):
-    """Mode 5 at head dims 65..128 runs ONE persistent kernel whose CTAs switch between dK/dV items and dQ items (a query
-    block's dQ is formed as soon as all its dS tiles have been written, while they are still in L2; bwd_pipe_sm100.cu).
-    Same role bodies, same arithmetic, same summation order as the two kernels run one after the other through the C ABI
-    (modes 6 then 7): bit-identical, 6 times in a row. (Head dim 64 runs the two kernels either way.)"""
-    import math
-    from fa2_triton_b200 import _lib
-    B, Hq, Hkv, Sq, Sk, D, causal = shape
-    lib = _lib.load()
-    q, k, v, do = generate_test_data(B, Sq, Sk, Hq, Hkv, D, torch.bfloat16, DEV, 31)
-    o, lse, scale, _ = fa2._flash_attn_forward(q, k, v, None, None, 0.0, causal, None, None)
-    s3, st = _lib.strides3, torch.cuda.current_stream().cuda_stream
-    Sp = math.ceil(Sq / 128) * 128
-    delta = torch.empty_like(lse)
-    _lib.check(lib.fa2_sm100_bwd_delta(o.data_ptr(), do.data_ptr(), delta.data_ptr(), B, Hq, Sq, D, s3(o), s3(do), Sp,
-                                       _lib.DTYPE_BF16, None, 0, st), "delta")
-    wsb = lib.fa2_sm100_bwd_workspace_bytes_gqa(B, Hq, Hkv, Sq, Sk, D, int(causal), _lib.DQ_DET_SPILL)
-
-    def run(modes):
-        ws = torch.empty(wsb, device=DEV, dtype=torch.uint8)
-        dq, dk, dv = torch.full_like(q, 7.0), torch.full_like(k, 7.0), torch.full_like(v, 7.0)
-        for mode in modes:
-            _lib.check(lib.fa2_sm100_bwd(do.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr(),
-                                         delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), wsb,
-                                         B, Hq, Hkv, Sq, Sk, D, s3(do), s3(q), s3(k), s3(v), s3(dq), s3(dk), s3(dv), Sp,
-                                         scale, int(causal), mode, _lib.DTYPE_BF16, _lib.DTYPE_BF16, st), "bwd")
-        torch.cuda.synchronize()
-        return dq, dk, dv
-
-    want = run((_lib.DQ_SPILL_DKDV, _lib.DQ_SPILL_DQ))
-    for _ in range(6):
-        got = run((_lib.DQ_DET_SPILL,))
-        for name, a, b in zip(("dQ", "dK", "dV"), got, want):
-            assert torch.equal(a, b), name
