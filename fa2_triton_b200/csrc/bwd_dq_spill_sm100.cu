@@ -43,13 +43,14 @@ struct DqSpillSmem {
 struct Item {
   int m, head, batch;
 };
-// work item w -> (query block, head, batch): query blocks of one (batch, head) are consecutive, longest first
-__device__ __forceinline__ Item item_of(int w, int n_q_blocks, int Hq) {
-  const int bh = w / n_q_blocks;
+// work item w -> (query block, head, batch): query blocks of one (batch, head) are consecutive, longest first; the last
+// heads are dealt block-major (fa2_kernels.cuh: tail_balanced_item)
+__device__ __forceinline__ Item item_of(int w, int n_q_blocks, int Hq, int B, int tail_heads) {
+  const ItemCoord c = tail_balanced_item(w, n_q_blocks, Hq, Hq * B, tail_heads);
   Item it;
-  it.m = n_q_blocks - 1 - (w - bh * n_q_blocks);
-  it.head = bh % Hq;
-  it.batch = bh / Hq;
+  it.m = n_q_blocks - 1 - c.x;
+  it.head = c.head;
+  it.batch = c.batch;
   return it;
 }
 
@@ -125,7 +126,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
         sched[slot] = (w < n_items) ? w : -1;
         mbar_arrive(&item_full[slot]);
         if (w >= n_items) break;
-        const Item it = item_of(w, n_q_blocks, p.Hq);
+        const Item it = item_of(w, n_q_blocks, p.Hq, p.B, p.tail_heads);
         const int head_kv = it.head / group;
         const int len = p.seqlens != nullptr ? min(max(p.seqlens[it.batch], 0), p.Sq) : 0;  // variable-length mode: this sequence's length
         const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
@@ -159,7 +160,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
         const int w = sched[slot];
         mbar_arrive(&item_empty[slot]);
         if (w < 0) break;
-        const Item it = item_of(w, n_q_blocks, p.Hq);
+        const Item it = item_of(w, n_q_blocks, p.Hq, p.B, p.tail_heads);
         const int len = p.seqlens != nullptr ? min(max(p.seqlens[it.batch], 0), p.Sq) : 0;  // variable-length mode: this sequence's length
         const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
                                               : visible_kv_blocks_of(it.m, p.Sq, p.Sk, p.causal);
@@ -195,7 +196,7 @@ fa2_bwd_dq_spill_kernel(const __grid_constant__ CUtensorMap tmap_k, const DqSpil
       const int w = sched[slot];
       mbar_arrive(&item_empty[slot]);
       if (w < 0) break;
-      const Item it = item_of(w, n_q_blocks, p.Hq);
+      const Item it = item_of(w, n_q_blocks, p.Hq, p.B, p.tail_heads);
       const int row = it.m * kBlk + r;
       const int len = p.seqlens != nullptr ? min(max(p.seqlens[it.batch], 0), p.Sq) : 0;  // variable-length mode: this sequence's length
         const int nblk = p.seqlens != nullptr ? visible_kv_blocks_of(it.m, len, len, p.causal)
@@ -262,7 +263,9 @@ static cudaError_t launch_bwd_dq_spill_t(const CUtensorMap& tk, const DqSpillPar
   const int n_items = ((p.Sq + kBlk - 1) / kBlk) * p.Hq * p.B;
   const int sms = current_sm_count();
   dim3 grid(n_items < sms ? n_items : sms);  // persistent: one CTA per SM
-  return launch_pdl(kernel, grid, dim3(kThreads), smem, stream, tk, p);
+  DqSpillParams pp = p;
+  pp.tail_heads = tail_heads_for(static_cast<size_t>(p.Sk) * D * 2, p.causal);  // a head's items stream its K
+  return launch_pdl(kernel, grid, dim3(kThreads), smem, stream, tk, pp);
 }
 
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream) {

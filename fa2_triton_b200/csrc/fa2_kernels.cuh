@@ -54,6 +54,50 @@ inline int current_sm_count() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Order in which a causal grid is worked through
+// ---------------------------------------------------------------------------------------------
+// The grids are (x = block of the sequence, heaviest first; y = head; z = batch) and the hardware hands out CTAs in
+// linear order: head by head, which keeps a head's K / V (forward, dQ) or Q / dO (dK/dV) in L2 while its blocks run.
+// Under a causal mask the blocks of a head differ in length by up to 32x, and with ~28 uneven CTAs per SM the last
+// wave leaves SMs idle: list-scheduling the real item lengths on 148 SMs gives 92 % (forward), 96 % (dK/dV, dQ) of the
+// ideal makespan at config 3. So the LAST `tail_heads` (batch, head) pairs are dealt block-major instead - the heaviest
+// blocks of all of them first, their lightest last (98-99 %) - as many heads as keep their streamed operands within
+// ~48 MB of L2. Which item a CTA works on changes, not what it computes: results are bit-identical.
+#ifndef FA2_TAIL_HEADS_MAX
+#define FA2_TAIL_HEADS_MAX 32
+#endif
+inline int tail_heads_for(size_t streamed_bytes_per_head, int causal) {
+  if (!causal || streamed_bytes_per_head == 0) return 0;
+  const size_t k = (48u << 20) / streamed_bytes_per_head;
+  const int t = static_cast<int>(k < FA2_TAIL_HEADS_MAX ? k : FA2_TAIL_HEADS_MAX);
+  return t < 2 ? 0 : t;
+}
+struct ItemCoord {
+  int x, head, batch;
+};
+// linear item index -> (x, head, batch) for nx blocks per head, ny heads, nbh = ny * batches (batch, head) pairs
+__host__ __device__ inline ItemCoord tail_balanced_item(int lin, int nx, int ny, int nbh, int tail_heads) {
+  const int K = tail_heads < nbh ? tail_heads : nbh;
+  const int body = (nbh - K) * nx;
+  int x, bh;
+  if (K < 2 || lin < body) {
+    bh = lin / nx;
+    x = lin - bh * nx;
+  } else {
+    const int r = lin - body;
+    x = r / K;
+    bh = nbh - K + (r - x * K);
+  }
+  return ItemCoord{x, bh % ny, bh / ny};
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ ItemCoord tail_balanced_cta(int tail_heads) {
+  const int nx = gridDim.x, ny = gridDim.y;
+  return tail_balanced_item(blockIdx.x + nx * (blockIdx.y + ny * blockIdx.z), nx, ny, ny * gridDim.z, tail_heads);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // forward (fwd_sm100.cu)
 // ---------------------------------------------------------------------------------------------
 // Variable-length batches (right-padded [B, S, ...] tensors, one length per batch element; query and key lengths
@@ -81,6 +125,7 @@ struct FwdParams {
   float scale_log2;  // softmax_scale * log2(e)
   int causal;
   int n_pairs;       // ceil(Sq / 256): one CTA per pair of 128-row query tiles
+  int tail_heads;    // (batch, head) pairs at the end of the grid that are dealt block-major (tail_balanced_cta); set by the launcher
   // extras (kernel variant kExt; all zero otherwise)
   BiasView bias;
   float bias_mul;       // 1 / softmax_scale: the bias joins the raw scores, which are multiplied by scale_log2 later
@@ -200,6 +245,7 @@ struct DkdvParams {
   float scale_log2;
   int causal;
   int* zero_word;         // work-item counter of the dQ kernel that follows on the stream: cleared by CTA (0, 0, 0), or nullptr
+  int tail_heads;         // (batch, kv head) pairs at the end of the grid that are dealt block-major; set by the launcher
   BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
   // kBias: a 16-bit bias whose rows TMA can address (16-byte aligned base and strides) is staged tile by tile through
   // shared memory with `bias_map` ((Sk, Sq, 1 | Hq, 1 | B), box 64 x 128); otherwise every thread loads its values itself
@@ -245,6 +291,7 @@ struct DqSpillParams {
   int d_actual;        // head dim of the tensors (multiple of 8, <= the kernel's D): columns beyond it are not stored
   const int* seqlens;  // variable-length mode, else nullptr
   const CUtensorMap* vmaps;
+  int tail_heads;      // (batch, head) pairs at the end of the item list that are dealt block-major; set by the launcher
 };
 cudaError_t launch_bwd_dq_spill(int D, bool bf16, const CUtensorMap& tk, const DqSpillParams& p, cudaStream_t stream);
 

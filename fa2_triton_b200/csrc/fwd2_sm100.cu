@@ -149,11 +149,13 @@ fa2_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // heaviest (largest row index) CTAs first: better tail behaviour under causal masking
+  // heaviest (largest row index) CTAs first, the last heads block-major: better tail behaviour under causal masking
+  // (fa2_kernels.cuh: tail_balanced_cta)
   const int cta_rows = kTiles * kBM;
-  const int slot = p.n_pairs - 1 - static_cast<int>(blockIdx.x);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
+  const ItemCoord cta = tail_balanced_cta(p.tail_heads);
+  const int slot = p.n_pairs - 1 - cta.x;
+  const int head = cta.head;
+  const int batch = cta.batch;
   const int head_kv = head / (p.Hq / p.Hkv);
   const int row0 = slot * cta_rows;
   // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
@@ -625,6 +627,8 @@ static cudaError_t launch_fwd2_t(const CUtensorMap& tq, const CUtensorMap& tk, c
   if (cudaError_t e = ensure_dynamic_smem<fa2_fwd2_kernel<D, kBf16, kBias>>(L::kDynBytes); e != cudaSuccess) return e;
   FwdParams pp = p;
   pp.n_pairs = (p.Sq + L::kTiles * kBM - 1) / (L::kTiles * kBM);
+  // a head's CTAs stream its K and V (GQA: shared by the group, counted per query head all the same - an upper bound)
+  pp.tail_heads = tail_heads_for(static_cast<size_t>(p.Sk) * D * 2 * 2, p.causal);
   dim3 grid(pp.n_pairs, p.Hq, p.B);
   return launch_pdl(fa2_fwd2_kernel<D, kBf16, kBias>, grid, dim3(L::kThreads), L::kDynBytes, stream, tq, tk, tv, to, pp);
 }
