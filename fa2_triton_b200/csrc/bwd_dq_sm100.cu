@@ -98,12 +98,13 @@ __device__ __forceinline__ int visible_kv_blocks(int row0, int Sq, int Sk, int c
 struct DqItem {
   int m, head, batch;
 };
-__device__ __forceinline__ DqItem dq_item(int w, int n_q_blocks, int Hq) {
-  const int bh = w / n_q_blocks;
+// The last heads are dealt block-major (fa2_kernels.cuh: tail_balanced_item).
+__device__ __forceinline__ DqItem dq_item(int w, int n_q_blocks, int Hq, int B, int tail_heads) {
+  const ItemCoord c = tail_balanced_item(w, n_q_blocks, Hq, Hq * B, tail_heads);
   DqItem it;
-  it.m = n_q_blocks - 1 - (w - bh * n_q_blocks);
-  it.head = bh % Hq;
-  it.batch = bh / Hq;
+  it.m = n_q_blocks - 1 - c.x;
+  it.head = c.head;
+  it.batch = c.batch;
   return it;
 }
 
@@ -210,7 +211,7 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         sched[slot] = (w < n_items) ? w : -1;
         mbar_arrive(&item_full[slot]);
         if (w >= n_items) break;
-        const DqItem it = dq_item(w, n_q_blocks, p.Hq);
+        const DqItem it = dq_item(w, n_q_blocks, p.Hq, p.B, p.tail_heads);
         const int row0 = it.m * kBlk;
         const int head_kv = it.head / group;
         const int nblk = visible_kv_blocks(row0, p.Sq, p.Sk, p.causal);
@@ -276,7 +277,7 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int w = sched[slot];
         mbar_arrive(&item_empty[slot]);
         if (w < 0) break;
-        const DqItem it = dq_item(w, n_q_blocks, p.Hq);
+        const DqItem it = dq_item(w, n_q_blocks, p.Hq, p.B, p.tail_heads);
         const int nblk = visible_kv_blocks(it.m * kBlk, p.Sq, p.Sk, p.causal);
         mbar_wait(q_full, t & 1);
         tcgen05_fence_after();
@@ -342,7 +343,7 @@ fa2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const int w = sched[slot];
       mbar_arrive(&item_empty[slot]);
       if (w < 0) break;
-      const DqItem it = dq_item(w, n_q_blocks, p.Hq);
+      const DqItem it = dq_item(w, n_q_blocks, p.Hq, p.B, p.tail_heads);
       const int row0 = it.m * kBlk;
       const int row = row0 + r;
       const int nblk = visible_kv_blocks(row0, p.Sq, p.Sk, p.causal);
@@ -500,8 +501,10 @@ static cudaError_t launch_bwd_dq_t(const CUtensorMap& tq, const CUtensorMap& tk,
   if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_dq_kernel<D, kBf16, kBias>>(smem); e != cudaSuccess) return e;
   const int n_items = ((p.Sq + kBlk - 1) / kBlk) * p.Hq * p.B;
   const int sms = current_sm_count();
-  dim3 grid(n_items < sms ? n_items : sms);  // persistent: one CTA per SM, items dealt round-robin
-  kernel<<<grid, kDqThreads, smem, stream>>>(tq, tk, tv, tdo, tdq, p);
+  dim3 grid(n_items < sms ? n_items : sms);  // persistent: one CTA per SM, items dealt dynamically
+  DqParams pp = p;
+  pp.tail_heads = tail_heads_for(static_cast<size_t>(p.Sk) * D * 2 * 2, p.causal);  // a head's items stream its K and V
+  kernel<<<grid, kDqThreads, smem, stream>>>(tq, tk, tv, tdo, tdq, pp);
   return cudaGetLastError();
 }
 

@@ -202,6 +202,7 @@ struct DqParams {
   int causal;
   BiasView bias;       // kernel variant kBias; ptr == nullptr otherwise
   int d_actual;        // head dim of the tensors (multiple of 8, <= the kernel's D): columns beyond it are not stored
+  int tail_heads;      // (batch, head) pairs at the end of the item list that are dealt block-major; set by the launcher
 };
 cudaError_t launch_bwd_dq(int D, bool bf16, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           const CUtensorMap& tdo, const CUtensorMap& tdq, const DqParams& p, cudaStream_t stream);

@@ -112,9 +112,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   // heaviest (largest row index) tile pairs first: better tail behaviour under causal masking
-  const int pair = p.n_pairs - 1 - static_cast<int>(blockIdx.x);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
+  const ItemCoord cta = tail_balanced_cta(p.tail_heads);  // the last heads block-major (fa2_kernels.cuh)
+  const int pair = p.n_pairs - 1 - cta.x;
+  const int head = cta.head;
+  const int batch = cta.batch;
   const int head_kv = head / (p.Hq / p.Hkv);
   const int row0 = pair * 2 * kBM;
   // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
@@ -651,7 +652,10 @@ static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
   if (cudaError_t e = ensure_dynamic_smem<fa2_fwd_kernel<D, kBf16, kExt>>(smem); e != cudaSuccess) return e;
   dim3 grid(p.n_pairs, p.Hq, p.B);
   const CUtensorMap& tbias = (kExt & 4) ? *p.bias_map : tq;  // placeholder when no bias goes through TMA
-  fa2_fwd_kernel<D, kBf16, kExt><<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, tbias, p);
+  FwdParams pp = p;
+  // a head's CTAs stream its K and V - and, with a per-head bias, its [Sq x Sk] bias: no block-major tail then
+  pp.tail_heads = (p.bias.ptr != nullptr && p.bias.sh != 0) ? 0 : tail_heads_for(static_cast<size_t>(p.Sk) * D * 2 * 2, p.causal);
+  fa2_fwd_kernel<D, kBf16, kExt><<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, tbias, pp);
   return cudaGetLastError();
 }
 
