@@ -193,3 +193,16 @@ extern "C" int fa2_probe_umma(const void* a, const void* b, float* d, int N, int
   p.a = a; p.b = b; p.d = d; p.N = N; p.K = K; p.a_mode = a_mode; p.b_mode = b_mode;
   return static_cast<int>(fa2::launch_probe(bf16, ta, tb, p, static_cast<cudaStream_t>(stream)));
 }
+
+// Host-side probe of the item order of the causal grids (fa2_kernels.cuh: tail_balanced_item): item `lin` of a grid with
+// nx blocks per head, ny heads and nbh (batch, head) pairs -> out = {x, head, batch}. tests/test_item_order.py checks
+// that the order is a permutation of the grid for every tail length.
+extern "C" void fa2_probe_tail_item(int lin, int nx, int ny, int nbh, int tail_heads, int* out) {
+  const fa2::ItemCoord c = fa2::tail_balanced_item(lin, nx, ny, nbh, tail_heads);
+  out[0] = c.x;
+  out[1] = c.head;
+  out[2] = c.batch;
+}
+extern "C" int fa2_probe_tail_heads_for(long long streamed_bytes_per_head, int causal) {
+  return fa2::tail_heads_for(static_cast<size_t>(streamed_bytes_per_head), causal);
+}
