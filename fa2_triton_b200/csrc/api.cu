@@ -391,7 +391,8 @@ size_t fa2_sm100_bwd_workspace_bytes(int B, int Hq, int Sq, int Sk, int D, int c
   }
   const size_t sq_pad = static_cast<size_t>(round_up(Sq, 128));
   const size_t accum = static_cast<size_t>(B) * Hq * sq_pad * D * sizeof(float);
-  const size_t sem = static_cast<size_t>(B) * Hq * (sq_pad / 128) * sizeof(int);
+  // one ticket per (batch, head, query tile) + the counter that numbers the CTAs of the ticket-ordered kernel as they start
+  const size_t sem = (static_cast<size_t>(B) * Hq * (sq_pad / 128) + 1) * sizeof(int);
   return accum + ((sem + 15) / 16) * 16;
 }
 
@@ -586,6 +587,7 @@ int bwd_impl(const void* dout, const void* q, const void* k, const void* v, cons
   p.scale_log2 = softmax_scale * kLog2e;
   p.causal = causal ? 1 : 0;
   p.deterministic = deterministic == FA2_DQ_FUSED_ORDERED ? 1 : 0;
+  p.order_ctr = p.deterministic ? p.dq_sem + static_cast<size_t>(B) * Hq * (sq_pad / 128) : nullptr;
   cudaError_t ce = cudaSuccess;
   const bool spill = deterministic == FA2_DQ_DET_SPILL || deterministic == FA2_DQ_SPILL_DKDV || deterministic == FA2_DQ_SPILL_DQ;
   const long long tiles_per_head = fa2::ds_tile_prefix((Sq + 127) / 128, Sq, Sk, causal ? 1 : 0);

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) fa2_delta_kernel(const DeltaParams p) {
     if (blockIdx.x == 0 && p.dq_sem != nullptr) {
       const int tiles = p.lse_stride / 128;
       for (int i = threadIdx.x; i < tiles; i += 256) p.dq_sem[bh * tiles + i] = 0;
+      if (bh == 0 && threadIdx.x == 0) p.dq_sem[static_cast<int64_t>(p.B) * p.Hq * tiles] = 0;  // the CTA-order counter
     }
   }
 }
@@ -223,9 +224,18 @@ fa2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
   const int n_kv_blocks = (p.Sk + kBlk - 1) / kBlk;
   const int n_q_blocks = (p.Sq + kBlk - 1) / kBlk;
-  const int nblk = n_kv_blocks - 1 - static_cast<int>(blockIdx.x);  // high key blocks are launched first
-  const int head_kv = blockIdx.y;
-  const int batch = blockIdx.z;
+  // Ticket-ordered mode: the CTA's place in the grid's linear order is drawn from a counter when it starts (see
+  // BwdParams::order_ctr) instead of being read off blockIdx - a CTA then only ever waits for CTAs that have started.
+  int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (p.order_ctr != nullptr) {
+    if (threadIdx.x == 0) tmem_slot[1] = static_cast<uint32_t>(atomicAdd(p.order_ctr, 1));
+    __syncthreads();
+    lin = static_cast<int>(tmem_slot[1]);
+  }
+  const int cta_x = lin % static_cast<int>(gridDim.x), cta_yz = lin / static_cast<int>(gridDim.x);
+  const int nblk = n_kv_blocks - 1 - cta_x;  // high key blocks are started first
+  const int head_kv = cta_yz % static_cast<int>(gridDim.y);
+  const int batch = cta_yz / static_cast<int>(gridDim.y);
   const int group = p.Hq / p.Hkv;
   const int shift = p.Sk - p.Sq;
   const int kv0 = nblk * kBlk;

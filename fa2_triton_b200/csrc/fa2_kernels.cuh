@@ -163,7 +163,7 @@ struct DeltaParams {
   int64_t o_strides[3];   // batch, head, seq (elements)
   int64_t do_strides[3];
   float* dq_accum;  // optional: backward workspace to clear ([B, Hq, lse_stride, D] fp32), or nullptr
-  int* dq_sem;      // optional: [B, Hq, lse_stride / 128] tickets to clear, or nullptr
+  int* dq_sem;      // optional: [B, Hq, lse_stride / 128] tickets (+ one CTA-order counter behind them) to clear, or nullptr
   const int* seqlens;  // variable-length mode: rows at or beyond a sequence's length get delta = 0 unread
 };
 cudaError_t launch_delta(bool bf16, const DeltaParams& p, cudaStream_t stream);
@@ -173,6 +173,10 @@ struct BwdParams {
   const float* delta;  // [B, Hq, lse_stride]
   float* dq_accum;     // [B, Hq, Sq_pad, D] fp32, tile-swizzled (see bwd_sm100.cu)
   int* dq_sem;         // [B, Hq, Sq_pad/128] ordered-reduction tickets (deterministic mode) or nullptr
+  // deterministic mode: the word behind the tickets. Every CTA draws its place in the grid's linear order from it as it
+  // STARTS, so a CTA that waits for a ticket only ever waits for CTAs that are already running or done - whatever order
+  // the hardware starts thread blocks in. Zero on entry (cleared with the tickets by the delta kernel).
+  int* order_ctr;
   int B, Hq, Hkv, Sq, Sk;
   int lse_stride;
   int sq_pad;  // ceil(Sq / 128) * 128

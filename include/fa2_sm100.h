@@ -119,7 +119,9 @@ int fa2_sm100_bwd_delta(const void* o, const void* dout, float* delta,
                         int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Bytes of scratch fa2_sm100_bwd needs. FA2_DQ_ATOMIC / FA2_DQ_FUSED_ORDERED: the fp32 dQ accumulator plus one int per
- * (batch, head, 128-row query tile). FA2_DQ_DETERMINISTIC / FA2_DQ_ONLY / FA2_DQ_NONE: 256 bytes (work-item counters of
+ * (batch, head, 128-row query tile) and one more (mode 2 numbers its thread blocks in the order they START with it, so a
+ * block that waits for its turn only ever waits for blocks that are running: no assumption about the order in which the
+ * hardware starts thread blocks). FA2_DQ_DETERMINISTIC / FA2_DQ_ONLY / FA2_DQ_NONE: 256 bytes (work-item counters of
  * the persistent kernels; cleared by the call itself). FA2_DQ_DET_SPILL (and 6, 7): 1 KB + B * Hq * (visible block pairs) * 32 KB
  * (`causal` decides which pairs are visible; B=4, H=32, S=4096 causal: 2.06 GiB).
  * The workspace must be 16-byte aligned. */

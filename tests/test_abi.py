@@ -36,9 +36,10 @@ def test_library_exports_every_declared_symbol():
 def test_workspace_size_formula():
     from fa2_triton_b200 import _lib
     lib = _lib.load()
-    # atomic / fused-ordered: fp32 accumulator over Sq padded to 128 + one ticket per (b, h, tile), 16-byte rounded
-    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 0) == 4 * 32 * 4096 * 128 * 4 + 4 * 32 * 32 * 4
-    assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 1000, 1000, 64, 0, 2) == 1024 * 64 * 4 + 32
+    # atomic / fused-ordered: fp32 accumulator over Sq padded to 128 + one ticket per (b, h, tile) + the counter that
+    # numbers the CTAs of the ticket-ordered kernel in the order they start, 16-byte rounded
+    assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 0) == 4 * 32 * 4096 * 128 * 4 + 4 * 32 * 32 * 4 + 16
+    assert lib.fa2_sm100_bwd_workspace_bytes(1, 1, 1000, 1000, 64, 0, 2) == 1024 * 64 * 4 + 48
     assert lib.fa2_sm100_bwd_workspace_bytes(0, 1, 1, 1, 64, 0, 0) == 0
     # deterministic / dQ only: dQ has its own kernel, nothing to accumulate into - just its scheduler's counter
     assert lib.fa2_sm100_bwd_workspace_bytes(4, 32, 4096, 4096, 128, 1, 1) == 256
