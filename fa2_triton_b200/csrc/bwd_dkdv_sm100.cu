@@ -183,14 +183,14 @@ fa2_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // causal: low key blocks are seen by the most query blocks - longest first; the last heads are dealt block-major
-  // (fa2_kernels.cuh: tail_balanced_cta)
-  const ItemCoord cta = tail_balanced_cta(p.tail_heads);
-  const int nblk = cta.x;
+  // Causal: low key blocks are seen by the most query blocks - longest first. (NOT the block-major tail of the other
+  // kernels, fa2_kernels.cuh: the remapped coordinates cost this kernel's compute warps registers they do not have -
+  // 4 -> 48 bytes of spills and +16 % cycles, against the 1.8 % the better tail is worth here.)
+  const int nblk = static_cast<int>(blockIdx.x);
   constexpr bool kBias = kExtra == 1, kVarlen = kExtra == 2, kSplit = kExtra == 3;
-  const int head_kv = cta.head;  // kSplit: the (kv head, part) index; the query heads below follow from it unchanged
+  const int head_kv = blockIdx.y;  // kSplit: the (kv head, part) index; the query heads below follow from it unchanged
   const int head_kv_src = kSplit ? head_kv / p.kv_split : head_kv;  // the kv head whose K / V rows are loaded
-  const int batch = cta.batch;
+  const int batch = blockIdx.z;
   const int kv0 = nblk * kBlk;
   // variable-length mode: this batch element's own length and tensor maps (bounded by it; batch coordinate 0)
   const int len = kVarlen ? min(max(p.seqlens[batch], 0), p.Sq) : 0;  // clamped like the tensor maps
@@ -700,11 +700,7 @@ static cudaError_t launch_bwd_dkdv_t(const CUtensorMap& tq, const CUtensorMap& t
   const CUtensorMap& tbias = p.bias_tma ? *p.bias_map : tq;  // placeholder when the bias is read through plain loads
   if (cudaError_t e = ensure_dynamic_smem<fa2_bwd_dkdv_kernel<D, kBf16, kSpill, kExtra>>(smem); e != cudaSuccess) return e;
   dim3 grid((p.Sk + kBlk - 1) / kBlk, p.Hkv * (kExtra == 3 ? p.kv_split : 1), p.B);
-  // a (key block, kv head) CTA streams Q and dO of the query heads it loops over
-  DkdvParams pp = p;
-  const int heads_per_cta = p.Hq / (p.Hkv * (kExtra == 3 ? p.kv_split : 1));
-  pp.tail_heads = tail_heads_for(static_cast<size_t>(p.Sq) * D * 2 * 2 * heads_per_cta, p.causal);
-  return launch_pdl(kernel, grid, dim3(kThreads), smem, stream, tq, tk, tv, tdo, tdk, tdv, tbias, pp);
+  return launch_pdl(kernel, grid, dim3(kThreads), smem, stream, tq, tk, tv, tdo, tdk, tdv, tbias, p);
 }
 
 cudaError_t launch_bwd_dkdv(int D, bool bf16, bool spill, const CUtensorMap& tq, const CUtensorMap& tk,

@@ -60,9 +60,15 @@ inline int current_sm_count() {
 // linear order: head by head, which keeps a head's K / V (forward, dQ) or Q / dO (dK/dV) in L2 while its blocks run.
 // Under a causal mask the blocks of a head differ in length by up to 32x, and with ~28 uneven CTAs per SM the last
 // wave leaves SMs idle: list-scheduling the real item lengths on 148 SMs gives 92 % (forward), 96 % (dK/dV, dQ) of the
-// ideal makespan at config 3. So the LAST `tail_heads` (batch, head) pairs are dealt block-major instead - the heaviest
-// blocks of all of them first, their lightest last (98-99 %) - as many heads as keep their streamed operands within
-// ~48 MB of L2. Which item a CTA works on changes, not what it computes: results are bit-identical.
+// ideal makespan at config 3. So the LAST heads are dealt block-major instead - the heaviest blocks of all of them
+// first, their lightest last (98-99 %) - as many heads as keep their streamed operands within ~48 MB of L2. Which item
+// a CTA works on changes, not what it computes: results are bit-identical.
+//
+// Two forms. The forward (a grid kernel): the tail is the last 2^k heads of the LAST batch element, so that the new
+// coordinates follow from blockIdx with shifts and masks alone, in the uniform datapath. The dQ kernels (persistent; items
+// decoded by a few threads): any number of (batch, head) pairs. NOT the dK/dV kernel: remapped coordinates - with a
+// division per CTA or without - cost its compute warps registers they do not have (4 -> 48-56 bytes of spills, +16 %
+// cycles under ncu; profiles/r02_experiments.txt, item 10), far more than the 1.8 % the better tail is worth there.
 #ifndef FA2_TAIL_HEADS_MAX
 #define FA2_TAIL_HEADS_MAX 32
 #endif
@@ -72,10 +78,27 @@ inline int tail_heads_for(size_t streamed_bytes_per_head, int causal) {
   const int t = static_cast<int>(k < FA2_TAIL_HEADS_MAX ? k : FA2_TAIL_HEADS_MAX);
   return t < 2 ? 0 : t;
 }
+// log2 of the largest power of two <= min(tail_heads, heads); 0 = no block-major tail
+inline int tail_log2_for(int tail_heads, int heads) {
+  const int t = tail_heads < heads ? tail_heads : heads;
+  int l = 0;
+  while ((2 << l) <= t) ++l;
+  return l;
+}
 struct ItemCoord {
   int x, head, batch;
 };
-// linear item index -> (x, head, batch) for nx blocks per head, ny heads, nbh = ny * batches (batch, head) pairs
+// grid kernels: block (x, y, z) of an (nx, ny, nz) grid -> the item it works on
+__host__ __device__ inline ItemCoord tail_balanced_block(int x, int y, int z, int nx, int ny, int nz, int tail_log2) {
+  // (branch-free, on purpose: with `if (a && b && c)` ptxas evaluated the condition per thread - predicates packed into
+  // general registers, 86 more LOP3 - instead of once in the uniform datapath)
+  const int h0 = ny - (1 << tail_log2);  // first head of the tail
+  const int in_tail = -static_cast<int>((tail_log2 > 0) & (z == nz - 1) & (y >= h0));  // all ones or zero
+  const int r = (y - h0) * nx + x;       // place inside the tail in launch order
+  const int xt = r >> tail_log2, ht = h0 + (r & ((1 << tail_log2) - 1));
+  return ItemCoord{x ^ ((x ^ xt) & in_tail), y ^ ((y ^ ht) & in_tail), z};
+}
+// persistent kernels: linear item index -> (x, head, batch) for nx blocks per head, ny heads, nbh = ny * batches pairs
 __host__ __device__ inline ItemCoord tail_balanced_item(int lin, int nx, int ny, int nbh, int tail_heads) {
   const int K = tail_heads < nbh ? tail_heads : nbh;
   const int body = (nbh - K) * nx;
@@ -91,9 +114,8 @@ __host__ __device__ inline ItemCoord tail_balanced_item(int lin, int nx, int ny,
   return ItemCoord{x, bh % ny, bh / ny};
 }
 #ifdef __CUDACC__
-__device__ __forceinline__ ItemCoord tail_balanced_cta(int tail_heads) {
-  const int nx = gridDim.x, ny = gridDim.y;
-  return tail_balanced_item(blockIdx.x + nx * (blockIdx.y + ny * blockIdx.z), nx, ny, ny * gridDim.z, tail_heads);
+__device__ __forceinline__ ItemCoord tail_balanced_cta(int tail_log2) {
+  return tail_balanced_block(blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, gridDim.z, tail_log2);
 }
 #endif
 
@@ -125,7 +147,7 @@ struct FwdParams {
   float scale_log2;  // softmax_scale * log2(e)
   int causal;
   int n_pairs;       // ceil(Sq / 256): one CTA per pair of 128-row query tiles
-  int tail_heads;    // (batch, head) pairs at the end of the grid that are dealt block-major (tail_balanced_cta); set by the launcher
+  int tail_log2;     // log2 of the heads at the end of the grid that are dealt block-major (tail_balanced_cta); set by the launcher
   // extras (kernel variant kExt; all zero otherwise)
   BiasView bias;
   float bias_mul;       // 1 / softmax_scale: the bias joins the raw scores, which are multiplied by scale_log2 later
@@ -250,7 +272,6 @@ struct DkdvParams {
   float scale_log2;
   int causal;
   int* zero_word;         // work-item counter of the dQ kernel that follows on the stream: cleared by CTA (0, 0, 0), or nullptr
-  int tail_heads;         // (batch, kv head) pairs at the end of the grid that are dealt block-major; set by the launcher
   BiasView bias;          // kernel variant kBias (one CTA per key block only); ptr == nullptr otherwise
   // kBias: a 16-bit bias whose rows TMA can address (16-byte aligned base and strides) is staged tile by tile through
   // shared memory with `bias_map` ((Sk, Sq, 1 | Hq, 1 | B), box 64 x 128); otherwise every thread loads its values itself

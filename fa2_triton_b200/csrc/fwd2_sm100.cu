@@ -152,7 +152,7 @@ fa2_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // heaviest (largest row index) CTAs first, the last heads block-major: better tail behaviour under causal masking
   // (fa2_kernels.cuh: tail_balanced_cta)
   const int cta_rows = kTiles * kBM;
-  const ItemCoord cta = tail_balanced_cta(p.tail_heads);
+  const ItemCoord cta = tail_balanced_cta(p.tail_log2);
   const int slot = p.n_pairs - 1 - cta.x;
   const int head = cta.head;
   const int batch = cta.batch;
@@ -628,7 +628,7 @@ static cudaError_t launch_fwd2_t(const CUtensorMap& tq, const CUtensorMap& tk, c
   FwdParams pp = p;
   pp.n_pairs = (p.Sq + L::kTiles * kBM - 1) / (L::kTiles * kBM);
   // a head's CTAs stream its K and V (GQA: shared by the group, counted per query head all the same - an upper bound)
-  pp.tail_heads = tail_heads_for(static_cast<size_t>(p.Sk) * D * 2 * 2, p.causal);
+  pp.tail_log2 = tail_log2_for(tail_heads_for(static_cast<size_t>(p.Sk) * D * 2 * 2, p.causal), p.Hq);
   dim3 grid(pp.n_pairs, p.Hq, p.B);
   return launch_pdl(fa2_fwd2_kernel<D, kBf16, kBias>, grid, dim3(L::kThreads), L::kDynBytes, stream, tq, tk, tv, to, pp);
 }

@@ -112,7 +112,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   // heaviest (largest row index) tile pairs first: better tail behaviour under causal masking
-  const ItemCoord cta = tail_balanced_cta(p.tail_heads);  // the last heads block-major (fa2_kernels.cuh)
+  const ItemCoord cta = tail_balanced_cta(p.tail_log2);  // the last heads block-major (fa2_kernels.cuh)
   const int pair = p.n_pairs - 1 - cta.x;
   const int head = cta.head;
   const int batch = cta.batch;
@@ -654,7 +654,7 @@ static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
   const CUtensorMap& tbias = (kExt & 4) ? *p.bias_map : tq;  // placeholder when no bias goes through TMA
   FwdParams pp = p;
   // a head's CTAs stream its K and V - and, with a per-head bias, its [Sq x Sk] bias: no block-major tail then
-  pp.tail_heads = (p.bias.ptr != nullptr && p.bias.sh != 0) ? 0 : tail_heads_for(static_cast<size_t>(p.Sk) * D * 2 * 2, p.causal);
+  pp.tail_log2 = (p.bias.ptr != nullptr && p.bias.sh != 0) ? 0 : tail_log2_for(tail_heads_for(static_cast<size_t>(p.Sk) * D * 2 * 2, p.causal), p.Hq);
   fa2_fwd_kernel<D, kBf16, kExt><<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, tbias, pp);
   return cudaGetLastError();
 }

@@ -203,6 +203,13 @@ extern "C" void fa2_probe_tail_item(int lin, int nx, int ny, int nbh, int tail_h
   out[1] = c.head;
   out[2] = c.batch;
 }
+extern "C" void fa2_probe_tail_block(int x, int y, int z, int nx, int ny, int nz, int tail_log2, int* out) {
+  const fa2::ItemCoord c = fa2::tail_balanced_block(x, y, z, nx, ny, nz, tail_log2);
+  out[0] = c.x;
+  out[1] = c.head;
+  out[2] = c.batch;
+}
+extern "C" int fa2_probe_tail_log2_for(int tail_heads, int heads) { return fa2::tail_log2_for(tail_heads, heads); }
 extern "C" int fa2_probe_tail_heads_for(long long streamed_bytes_per_head, int causal) {
   return fa2::tail_heads_for(static_cast<size_t>(streamed_bytes_per_head), causal);
 }
