@@ -72,9 +72,12 @@ inline int current_sm_count() {
 #ifndef FA2_TAIL_HEADS_MAX
 #define FA2_TAIL_HEADS_MAX 32
 #endif
+#ifndef FA2_TAIL_L2_MB
+#define FA2_TAIL_L2_MB 48  // L2 budget for the streamed operands of the tail's heads
+#endif
 inline int tail_heads_for(size_t streamed_bytes_per_head, int causal) {
   if (!causal || streamed_bytes_per_head == 0) return 0;
-  const size_t k = (48u << 20) / streamed_bytes_per_head;
+  const size_t k = (static_cast<size_t>(FA2_TAIL_L2_MB) << 20) / streamed_bytes_per_head;
   const int t = static_cast<int>(k < FA2_TAIL_HEADS_MAX ? k : FA2_TAIL_HEADS_MAX);
   return t < 2 ? 0 : t;
 }
