@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define FA2_SM100_ABI_VERSION 12
+#define FA2_SM100_ABI_VERSION 13
 
 #define FA2_DTYPE_FP16 16
 #define FA2_DTYPE_BF16 17

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/fa2_sm100.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.fa2_sm100_version() == 12
+    assert lib.fa2_sm100_version() == 13
 
 
 def test_workspace_size_formula():
